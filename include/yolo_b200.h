@@ -1,0 +1,161 @@
+/*
+ * yolo_b200.h - C ABI of the B200-native YOLOv3 detection hot path (drop-in for the MXNet/Gluon
+ * path of n8886919/YOLO).  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Every entry point returns an int status (0 = OK, negative = YOLO_E_*), never aborts; the text of
+ * the last failure on a handle is available through yolo_last_error().  All device work is
+ * asynchronous on the cudaStream_t passed as `stream` (void* so the header needs no CUDA include).
+ * A handle is not internally locked: "forward on thread A, decode of a copied output on thread B"
+ * is safe (reference threading contract, car/video_node.py:131-177); concurrent calls on the SAME
+ * handle must be serialised by the caller.
+ *
+ * Reference interfaces replaced (paths under the reference repo):
+ *   yolo_create / yolo_destroy      <- YOLO.__init__ + _init_net      car/YOLO.py:49-110,
+ *                                      CarLPNet                       car_and_LP/YOLO.py:47-61,
+ *                                      LPDenseNet                     licence_plate/LP_detection.py:59-97
+ *   yolo_param_* / yolo_load_param  <- yolo_gluon.init_NN             yolo_modules/yolo_gluon.py:172-201
+ *                                      yolo_gluon.init_executor       yolo_modules/yolo_gluon.py:204-242
+ *   yolo_forward                    <- net.forward(is_train=False, data=nd_img)
+ *                                      car/video_node.py:230-231, licence_plate/LPD_video_node.py:78-79
+ *   yolo_decode_top1                <- YOLO.predict                   car/YOLO.py:568-597
+ *                                      (+ _init_syxhw :123-155, _yxhw_to_ltrb :552-566, merge_and_slice :841-849)
+ *   yolo_decode_nms                 <- north-star extension (the reference has no NMS);
+ *                                      IoU form of yolo_gluon.get_iou yolo_modules/yolo_gluon.py:158-167
+ *   yolo_decode_lp                  <- YOLO.predict_LP                car_and_LP/YOLO.py:133-169 (mode 0)
+ *                                      LicencePlateDetectioin.predict_LP licence_plate/LP_detection.py:147-162 (mode 1)
+ *   yolo_predict_host               <- cv_img_2_ndarray + net.forward + predict + asnumpy
+ *                                      yolo_modules/yolo_gluon.py:335-357, car/YOLO.py:597
+ */
+#ifndef YOLO_B200_H_
+#define YOLO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YOLO_OK          0
+#define YOLO_E_BADARG   -1
+#define YOLO_E_SHAPE    -2
+#define YOLO_E_CUDA     -3
+#define YOLO_E_NCCL     -4
+#define YOLO_E_OOM      -5
+#define YOLO_E_STATE    -6
+#define YOLO_E_UNSUPPORTED -7
+
+#define YOLO_MAX_STAGES  8
+#define YOLO_MAX_SCALES  3
+#define YOLO_MAX_ANCHORS 8
+#define YOLO_MAX_BLOCKS  8
+
+/* net_type */
+#define YOLO_NET_CARNET      0   /* BasicYOLONet topology + CarNet forward */
+#define YOLO_NET_CARLPNET    1   /* CarNet + licence-plate pose branch */
+#define YOLO_NET_LPDENSENET  2   /* DenseNet licence-plate detector */
+
+/* precision: arithmetic of the convolution path */
+#define YOLO_PREC_FP32    0   /* fp32 FFMA implicit GEMM (parity grade)            */
+#define YOLO_PREC_BF16    1   /* bf16 operands, fp32 accumulate, tcgen05 tensor cores */
+#define YOLO_PREC_TF32X3  2   /* error-compensated 3xTF32 on tcgen05 (fp32 grade)   */
+
+/* input layouts accepted by yolo_forward */
+#define YOLO_IN_NCHW_F32  0   /* (B,3,H,W) fp32 in [0,1] - what cv_img_2_ndarray produces */
+#define YOLO_IN_NHWC_U8   1   /* (B,H,W,3) uint8 camera frames; /255 fused into the stem  */
+
+typedef struct yolo_handle yolo_handle;
+
+/* Mirrors the reference's spec.yaml schema (car/v1/spec.yaml, licence_plate/v2/spec.yaml). */
+typedef struct yolo_spec {
+  int32_t net_type;
+  int32_t height, width;                 /* spec `size` */
+  int32_t n_layers;                      /* len(spec `layers`)  */
+  int32_t layers[YOLO_MAX_STAGES];
+  int32_t channels[YOLO_MAX_STAGES + 1]; /* len = n_layers + 1  */
+  int32_t n_scales, n_anchors;           /* spec `all_anchors` is (n_scales, n_anchors, 2) as (h, w) */
+  float   anchors[YOLO_MAX_SCALES][YOLO_MAX_ANCHORS][2];
+  int32_t channels_per_anchor;           /* slice_point[-1]; slices are fixed at [1,3,5,6,C] */
+  int32_t lp_channels;                   /* LP_slice_point[-1] (10) */
+  float   lp_r_max[3];
+  int32_t lp_num_class;
+  /* LPDenseNet */
+  int32_t num_init_features, growth_rate, bn_size;
+  int32_t n_blocks;
+  int32_t block_config[YOLO_MAX_BLOCKS];
+  /* execution */
+  int32_t precision;
+  int32_t max_batch;
+} yolo_spec;
+
+/* Geometry needed by the decode kernels; independent of any network handle. */
+typedef struct yolo_decode_geom {
+  int32_t height, width;
+  int32_t n_scales, n_anchors, channels_per_anchor;
+  int32_t step[YOLO_MAX_SCALES];         /* stride of each scale, shallow -> deep */
+  float   anchors[YOLO_MAX_SCALES][YOLO_MAX_ANCHORS][2];
+} yolo_decode_geom;
+
+typedef struct yolo_nms_params {
+  float   score_thr;   /* keep candidates with sigmoid(score) > score_thr */
+  float   iou_thr;     /* suppress same-class boxes with IoU > iou_thr   */
+  int32_t max_out;     /* rows written per image                          */
+  int32_t max_cand;    /* candidates entering suppression (<= 1024)       */
+} yolo_nms_params;
+
+const char* yolo_version(void);
+
+int  yolo_create(const yolo_spec* spec, int device, yolo_handle** out);
+int  yolo_destroy(yolo_handle* h);
+const char* yolo_last_error(const yolo_handle* h);   /* h may be NULL: last create() failure */
+
+/* Parameters.  Enumerate in canonical order; shapes are (O,I,kh,kw) for conv weights, (C) otherwise. */
+int  yolo_param_count(const yolo_handle* h);
+int  yolo_param_info(const yolo_handle* h, int index, const char** name, int32_t shape[4], int32_t* ndim);
+int  yolo_load_param(yolo_handle* h, const char* name, const float* host, size_t n_elems);
+int  yolo_finalize_params(yolo_handle* h, void* stream);   /* fold BN, repack, upload; requires all params */
+
+/* Activation workspace: caller-owned device memory (e.g. a torch uint8 tensor). */
+size_t yolo_workspace_bytes(const yolo_handle* h, int batch);
+int  yolo_set_workspace(yolo_handle* h, void* device_ptr, size_t bytes);
+
+/* Outputs of forward: n_out tensors; shape query returns per-image dims. */
+int  yolo_output_count(const yolo_handle* h);
+int  yolo_output_shape(const yolo_handle* h, int index, int32_t shape[4], int32_t* ndim); /* without batch dim */
+
+/* Forward.  `input` and every outputs[i] are device pointers; outputs are fp32:
+ *   CARNET     : n_scales heads (B, H_s*W_s, A, C) shallow -> deep
+ *   CARLPNET   : the same + LP map (B, H_0, W_0, lp_channels)
+ *   LPDENSENET : NCHW (B, 7+lp_num_class, H/32, W/32)                                            */
+int  yolo_forward(yolo_handle* h, const void* input, int batch, int in_layout,
+                  void* const* outputs, void* stream);
+
+/* Debug/parity: copy an internal activation (by oracle layer name) to host as NCHW fp32. */
+int  yolo_debug_activation(yolo_handle* h, const char* layer_name, int batch, float* host_nchw, size_t n_elems);
+
+/* Decode + selection (fused, one launch).  heads: device fp32, shallow -> deep.
+ * out_rows (B, C) fp32 = [sigmoid(score), y, x, h, w, rotate, class logits...]; out_idx (B) int32 flat index. */
+int  yolo_decode_top1(const yolo_decode_geom* g, const void* const* heads, int batch,
+                      float* out_rows, int32_t* out_idx, void* stream);
+/* out_rows (B, max_out, C), out_idx (B, max_out), out_count (B). out_count[b] < 0: candidate overflow (>4096). */
+int  yolo_decode_nms(const yolo_decode_geom* g, const void* const* heads, int batch,
+                     const yolo_nms_params* p, float* out_rows, int32_t* out_idx, int32_t* out_count,
+                     void* stream);
+/* Licence-plate pose decode.  mode 0: lp (B,Hs,Ws,ch) NHWC, argmax of sigmoid(score), out (B,7);
+ * mode 1: lp (B,ch,Hs,Ws) NCHW, argmax of the raw score, out (B,ch).  out_idx (B) may be NULL. */
+int  yolo_decode_lp(const void* lp, int batch, int hs, int ws, int ch, int mode, const float r_max[3],
+                    float* out_rows, int32_t* out_idx, void* stream);
+
+/* End-to-end convenience with HOST buffers (pinned recommended): H2D, forward, decode_top1, D2H, sync.
+ * CARNET / CARLPNET only.  host_rows (B, C) ; host_idx (B) may be NULL. */
+int  yolo_predict_host(yolo_handle* h, const void* host_input, int batch, int in_layout,
+                       float* host_rows, int32_t* host_idx, void* stream);
+
+/* Introspection used by bench.py: launches issued by the last forward()/decode call, conv FLOPs per image. */
+int    yolo_last_launch_count(const yolo_handle* h);
+double yolo_conv_flops_per_image(const yolo_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* YOLO_B200_H_ */

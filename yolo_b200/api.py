@@ -1,0 +1,293 @@
+"""Python host side of yolo_b200: thin objects over the C ABI.
+
+PyTorch is used only as the device-memory container (workspace, inputs, outputs) and for streams.
+``Net`` mirrors the executor the reference drivers hold in ``self.net`` (``yolo_gluon.init_executor``,
+yolo_modules/yolo_gluon.py:204-242): ``net.forward(is_train=False, data=...)`` returns the list of head
+tensors, each with ``.shape`` / ``.wait_to_read()`` / ``.asnumpy()`` / ``.copy()`` like an mx NDArray.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (DecodeGeom, NmsParams, YoloSpec, check, IN_NCHW_F32, IN_NHWC_U8, NET_CARNET, NET_CARLPNET,
+                   NET_LPDENSENET, PRECISIONS)
+
+NET_TYPES = {"carnet": NET_CARNET, "carlpnet": NET_CARLPNET, "lpdensenet": NET_LPDENSENET}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("yolo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class NDArray:
+    """Minimal mx.nd.NDArray look-alike over a torch CUDA tensor."""
+
+    def __init__(self, t: torch.Tensor):
+        self.t = t
+
+    @property
+    def shape(self):
+        return tuple(self.t.shape)
+
+    def wait_to_read(self):
+        torch.cuda.current_stream(self.t.device).synchronize()
+        return self
+
+    def asnumpy(self):
+        return self.t.detach().cpu().numpy()
+
+    def copy(self):
+        return NDArray(self.t.clone())
+
+    def __len__(self):
+        return self.t.shape[0]
+
+
+def _as_tensor(x):
+    return x.t if isinstance(x, NDArray) else x
+
+
+def init_steps(spec):
+    """car/YOLO.py:112-116."""
+    nd, npyr = len(spec["layers"]), len(spec["all_anchors"])
+    start = nd - npyr + 1
+    return [2 ** (start + i) for i in range(npyr)]
+
+
+def make_c_spec(net_type, spec, precision="fp32", max_batch=1):
+    s = YoloSpec()
+    s.net_type = NET_TYPES[net_type]
+    s.height, s.width = int(spec["size"][0]), int(spec["size"][1])
+    s.precision = PRECISIONS[precision]
+    s.max_batch = int(max_batch)
+    s.bn_size = int(spec.get("bn_size", 4))
+    if net_type in ("carnet", "carlpnet"):
+        layers, channels, anchors = spec["layers"], spec["channels"], spec["all_anchors"]
+        if len(layers) != len(channels) - 1:
+            raise ValueError("len(channels) should equal to len(layers) + 1, given {} vs {}".format(len(channels), len(layers)))
+        if len(layers) > _lib.MAX_STAGES or len(anchors) > _lib.MAX_SCALES or len(anchors[0]) > _lib.MAX_ANCHORS:
+            raise ValueError("spec exceeds compiled limits")
+        sp = list(spec["slice_point"])
+        if sp[:4] != [1, 3, 5, 6]:
+            raise ValueError(f"slice_point {sp} unsupported: the decode kernel is built for [1,3,5,6,C] (car/v1/spec.yaml:6)")
+        s.n_layers = len(layers)
+        for i, v in enumerate(layers):
+            s.layers[i] = int(v)
+        for i, v in enumerate(channels):
+            s.channels[i] = int(v)
+        s.n_scales, s.n_anchors = len(anchors), len(anchors[0])
+        for i, sc in enumerate(anchors):
+            for j, (ah, aw) in enumerate(sc):
+                s.anchors[i][j][0], s.anchors[i][j][1] = float(ah), float(aw)
+        s.channels_per_anchor = int(sp[-1])
+    if net_type in ("carlpnet", "lpdensenet"):
+        s.lp_channels = int(spec["LP_slice_point"][-1])
+        for i in range(3):
+            s.lp_r_max[i] = float(spec["LP_r_max"][i])
+        s.lp_num_class = int(spec["LP_num_class"])
+    if net_type == "lpdensenet":
+        s.num_init_features, s.growth_rate = int(spec["num_init_features"]), int(spec["growth_rate"])
+        cfg = spec["block_config"]
+        s.n_blocks = len(cfg)
+        for i, v in enumerate(cfg):
+            s.block_config[i] = int(v)
+    return s
+
+
+def make_geom(spec, steps=None):
+    g = DecodeGeom()
+    g.height, g.width = int(spec["size"][0]), int(spec["size"][1])
+    anchors = spec["all_anchors"]
+    g.n_scales, g.n_anchors = len(anchors), len(anchors[0])
+    g.channels_per_anchor = int(spec["slice_point"][-1])
+    steps = steps or init_steps(spec)
+    for i, st in enumerate(steps):
+        g.step[i] = int(st)
+    for i, sc in enumerate(anchors):
+        for j, (ah, aw) in enumerate(sc):
+            g.anchors[i][j][0], g.anchors[i][j][1] = float(ah), float(aw)
+    return g
+
+
+class Net:
+    """A network instance on one GPU (one process per GPU; see yolo_b200.parallel for sharding)."""
+
+    def __init__(self, net_type, spec, precision="fp32", max_batch=1, device=0):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.net_type, self.spec, self.precision, self.max_batch = net_type, spec, precision, int(max_batch)
+        self.device = torch.device("cuda", device)
+        self._h = C.c_void_p()
+        cs = make_c_spec(net_type, spec, precision, max_batch)
+        check(self.lib.yolo_create(C.byref(cs), device, C.byref(self._h)))
+        self._ws = None
+        self._pinned = None
+        self.out_shapes = []
+        for i in range(self.lib.yolo_output_count(self._h)):
+            shp, nd = (C.c_int32 * 4)(), C.c_int32()
+            check(self.lib.yolo_output_shape(self._h, i, C.byref(shp), C.byref(nd)), self._h)
+            self.out_shapes.append(tuple(shp[k] for k in range(nd.value)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                self.lib.yolo_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- parameters (yolo_gluon.init_NN, yolo_modules/yolo_gluon.py:172-201) -------------------------
+    def param_shapes(self):
+        out = []
+        for i in range(self.lib.yolo_param_count(self._h)):
+            name, shp, nd = C.c_char_p(), (C.c_int32 * 4)(), C.c_int32()
+            check(self.lib.yolo_param_info(self._h, i, C.byref(name), C.byref(shp), C.byref(nd)), self._h)
+            out.append((name.value.decode(), tuple(shp[k] for k in range(nd.value))))
+        return out
+
+    def load_params(self, params: dict):
+        for name, shape in self.param_shapes():
+            if name not in params:
+                raise KeyError(f"missing parameter {name}")
+            a = np.ascontiguousarray(np.asarray(params[name], dtype=np.float32))
+            if tuple(a.shape) != shape:
+                raise ValueError(f"{name}: expected shape {shape}, got {tuple(a.shape)}")
+            check(self.lib.yolo_load_param(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.size), self._h)
+        with torch.cuda.device(self.device):
+            check(self.lib.yolo_finalize_params(self._h, _stream_ptr(self.device)), self._h)
+            self._ensure_workspace()
+        return self
+
+    def _ensure_workspace(self):
+        if self._ws is None:
+            n = self.lib.yolo_workspace_bytes(self._h, self.max_batch)
+            self._ws = torch.empty(max(n, 1024) + 1024, dtype=torch.uint8, device=self.device)
+            ptr = (self._ws.data_ptr() + 1023) & ~1023
+            check(self.lib.yolo_set_workspace(self._h, C.c_void_p(ptr), n), self._h)
+
+    # ---- forward (car/video_node.py:230-231) ------------------------------------------------------
+    def _to_device(self, data):
+        data = _as_tensor(data)
+        if isinstance(data, np.ndarray):
+            t = torch.from_numpy(data)
+            if self._pinned is None or self._pinned.numel() < t.numel() * t.element_size():
+                self._pinned = torch.empty(t.numel() * t.element_size(), dtype=torch.uint8).pin_memory()
+            stage = self._pinned[: t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+            stage.copy_(t)
+            return stage.to(self.device, non_blocking=True)
+        if not data.is_cuda:
+            return data.to(self.device, non_blocking=True)
+        return data
+
+    def forward(self, is_train=False, data=None):
+        if is_train:
+            raise NotImplementedError("training forward goes through the train-step API")
+        x = self._to_device(data)
+        H, W = self.spec["size"]
+        if x.dtype == torch.float32 and x.dim() == 4 and tuple(x.shape[1:]) == (3, H, W):
+            layout = IN_NCHW_F32
+        elif x.dtype == torch.uint8 and x.dim() == 4 and tuple(x.shape[1:]) == (H, W, 3):
+            layout = IN_NHWC_U8
+        else:
+            raise ValueError(f"input must be (B,3,{H},{W}) float32 or (B,{H},{W},3) uint8, got {tuple(x.shape)} {x.dtype}")
+        x = x.contiguous()
+        B = x.shape[0]
+        with torch.cuda.device(self.device):
+            outs = [torch.empty((B,) + s, dtype=torch.float32, device=self.device) for s in self.out_shapes]
+            ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+            check(self.lib.yolo_forward(self._h, C.c_void_p(x.data_ptr()), B, layout, ptrs, _stream_ptr(self.device)), self._h)
+        self._keep = x                       # keep the input alive until the stream has consumed it
+        return [NDArray(o) for o in outs]
+
+    def predict_host(self, frames: torch.Tensor):
+        """One C call: H2D + forward + decode_top1 + D2H (yolo_predict_host).  ``frames`` is a (pinned) host tensor."""
+        B = frames.shape[0]
+        layout = IN_NCHW_F32 if frames.dtype == torch.float32 else IN_NHWC_U8
+        C_ = int(self.spec["slice_point"][-1])
+        rows = np.empty((B, C_), np.float32)
+        idx = np.empty((B,), np.int32)
+        with torch.cuda.device(self.device):
+            check(self.lib.yolo_predict_host(self._h, C.c_void_p(frames.data_ptr()), B, layout, rows.ctypes.data_as(C.c_void_p),
+                                             idx.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)), self._h)
+        return rows, idx
+
+    def activation(self, name, shape):
+        """Copy an internal activation (oracle layer name) to host as NCHW fp32 of the given shape (parity tests)."""
+        out = np.empty(shape, np.float32)
+        check(self.lib.yolo_debug_activation(self._h, name.encode(), shape[0], out.ctypes.data_as(C.c_void_p), out.size), self._h)
+        return out
+
+    @property
+    def launches(self):
+        return self.lib.yolo_last_launch_count(self._h)
+
+    @property
+    def conv_flops_per_image(self):
+        return self.lib.yolo_conv_flops_per_image(self._h)
+
+
+# ---- decode entry points (no network handle needed) ------------------------------------------------------
+def _head_ptrs(heads):
+    ts = [_as_tensor(h) for h in heads]
+    for t in ts:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("heads must be contiguous float32 CUDA tensors")
+    return ts, (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+def decode_top1(spec, heads, steps=None):
+    """car/YOLO.py:568-597 as one kernel.  Returns (rows (B,C) cuda fp32, idx (B,) cuda int32)."""
+    lib = _lib.load()
+    ts, ptrs = _head_ptrs(heads)
+    B, dev = ts[0].shape[0], ts[0].device
+    g = make_geom(spec, steps)
+    rows = torch.empty((B, g.channels_per_anchor), dtype=torch.float32, device=dev)
+    idx = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.yolo_decode_top1(C.byref(g), ptrs, B, C.c_void_p(rows.data_ptr()), C.c_void_p(idx.data_ptr()), _stream_ptr(dev)))
+    return rows, idx
+
+
+def decode_nms(spec, heads, score_thr=0.5, iou_thr=0.45, max_out=100, max_cand=1024, steps=None):
+    lib = _lib.load()
+    ts, ptrs = _head_ptrs(heads)
+    B, dev = ts[0].shape[0], ts[0].device
+    g = make_geom(spec, steps)
+    p = NmsParams(float(score_thr), float(iou_thr), int(max_out), int(max_cand))
+    rows = torch.zeros((B, max_out, g.channels_per_anchor), dtype=torch.float32, device=dev)
+    idx = torch.full((B, max_out), -1, dtype=torch.int32, device=dev)
+    cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.yolo_decode_nms(C.byref(g), ptrs, B, C.byref(p), C.c_void_p(rows.data_ptr()), C.c_void_p(idx.data_ptr()),
+                                  C.c_void_p(cnt.data_ptr()), _stream_ptr(dev)))
+    return rows, idx, cnt
+
+
+def decode_lp(lp, mode, r_max):
+    """mode 0: (B,Hs,Ws,ch) NHWC, sigmoid-score argmax -> (B,7); mode 1: (B,ch,Hs,Ws) NCHW, raw-score argmax -> (B,ch)."""
+    lib = _lib.load()
+    t = _as_tensor(lp)
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4):
+        raise ValueError("lp must be a contiguous 4-d float32 CUDA tensor")
+    if mode == 0:
+        B, hs, ws, ch = t.shape
+        nout = 7
+    else:
+        B, ch, hs, ws = t.shape
+        nout = ch
+    rm = (C.c_float * 3)(*[float(v) for v in r_max])
+    rows = torch.empty((B, nout), dtype=torch.float32, device=t.device)
+    idx = torch.empty((B,), dtype=torch.int32, device=t.device)
+    with torch.cuda.device(t.device):
+        check(lib.yolo_decode_lp(C.c_void_p(t.data_ptr()), B, hs, ws, ch, mode, C.byref(rm), C.c_void_p(rows.data_ptr()),
+                                 C.c_void_p(idx.data_ptr()), _stream_ptr(t.device)))
+    return rows, idx

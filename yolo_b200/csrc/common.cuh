@@ -1,0 +1,57 @@
+// Shared helpers for the yolo_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/yolo_b200.h"
+
+namespace yb {
+
+// Thread-local text of the last failure for calls that have no handle (decode entry points, create()).
+std::string& tls_error();
+int fail(int code, const char* fmt, ...);
+
+#define YB_CUDA(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return yb::fail(YOLO_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,            \
+                      cudaGetErrorString(_e));                                            \
+  } while (0)
+
+// Global launch counter (kernels of THIS library), read by yolo_last_launch_count().
+extern thread_local int g_launches;
+
+enum Act : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
+enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+
+// One convolution (+ fused prologue / epilogue) as executed by the kernels.  Activations are NHWC;
+// a tensor may be a channel slice [coff, coff+C) of a wider buffer with `cpitch` channels per pixel
+// (this is how route concat and DenseNet concat are realised without copies).
+struct ConvDesc {
+  // input
+  const void* in;  int in_dtype;  int N, H, W, Cin;  int in_cpitch, in_coff;
+  // filter
+  int kh, kw, stride, pad;  int Cout;
+  const float* w_f32;          // [kh*kw*Cin][CoutPad4] fp32 (SIMT path), k = (r*kw+s)*Cin + c
+  int cout_pad;                // row pitch of w_f32
+  // prologue on the input (DenseNet pre-activation BN->ReLU): v = relu(v*pre_scale[c] + pre_shift[c])
+  const float* pre_scale;  const float* pre_shift;
+  // epilogue: y = act(acc*scale[o] + shift[o]) (+ residual)
+  const float* scale;  const float* shift;  int act;
+  const void* res;  int res_cpitch, res_coff;   // same dtype as out
+  // output
+  void* out;  int out_dtype;  int Ho, Wo;  int out_cpitch, out_coff;
+  int upsample2;               // write every output pixel to the 2x2 block of a (2Ho, 2Wo) map
+  int out_nchw;                // fp32 only: store as (N, Cout, Ho, Wo)
+};
+
+// in_layout: 0 = NHWC of in_dtype, 1 = NCHW fp32 (stem only), 2 = NHWC uint8 scaled by 1/255 (stem only)
+int launch_conv_simt(const ConvDesc& d, int in_layout, cudaStream_t st);
+int launch_pool(const void* in, void* out, int dtype, int N, int H, int W, int C, int in_cpitch, int in_coff,
+                int out_cpitch, int out_coff, int k, int stride, int pad, int is_max, cudaStream_t st);
+
+}  // namespace yb

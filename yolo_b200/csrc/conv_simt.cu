@@ -1,0 +1,320 @@
+// fp32-accurate implicit-GEMM convolution on the CUDA cores (FFMA), NHWC, with the fused
+// prologue/epilogue set the reference's blocks need.  This is the YOLO_PREC_FP32 (parity-grade) path
+// and the fallback for shapes the tcgen05 kernel does not take (Cin % 64 != 0: stems, DenseNet).
+//
+// Replaces the MXNet operator chains (reference, file:line):
+//   gluoncv _conv2d = Convolution(no bias) -> BatchNorm(eps 1e-5) -> LeakyReLU(0.1)    yolo_modules/basic_yolo.py:20-26,118-121
+//   DarknetBasicBlockV3 residual add (elemwise_add)                                     yolo_modules/basic_yolo.py:26
+//   _upsample (repeat x2) + concat(dim=1)                                               car/utils.py:92-93
+//   YOLOOutput: 1x1 Convolution + bias, transpose(0,2,3,1)                              yolo_modules/basic_yolo.py:98-103
+//   DenseNet BN -> ReLU -> conv (pre-activation), concat([x, new])                      licence_plate/LP_detection.py:70-93
+//   MaxPool 3/2 p1, AvgPool 2/2                                                         licence_plate/LP_detection.py:74
+//   cv_img_2_ndarray (/255, HWC->CHW) fused into the stem's gather                      yolo_modules/yolo_gluon.py:335-357
+//
+// GEMM view: M = N*Ho*Wo output pixels, N = Cout, K = kh*kw*Cin with k = (r*kw + s)*Cin + c.
+// CTA tile 128(M) x 64(N) x 16(K), 256 threads, 8x4 accumulators per thread, register-staged
+// double buffering of the shared-memory tiles.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace yb {
+
+constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
+constexpr int AS_PITCH = BM + 4;
+
+enum InLayout : int { IN_NHWC = 0, IN_NCHW_F32 = 1, IN_NHWC_U8 = 2 };
+
+struct ConvKArgs {
+  ConvDesc d;
+  int in_layout;
+  int M, K;
+};
+
+__device__ __forceinline__ float ld_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+__device__ __forceinline__ void load8(const float* p, float v[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float v[8]) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+
+__device__ __forceinline__ void store4(float* p, const float v[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float v[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<unsigned*>(&a);
+  u.y = *reinterpret_cast<unsigned*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ void store1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void load4(const float* p, float v[4]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float v[4]) {
+  uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template <typename TIn, typename TOut, bool VEC>
+__global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ ConvKArgs args) {
+  const ConvDesc& d = args.d;
+  __shared__ __align__(16) float As[2][BK][AS_PITCH];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int M = args.M, K = args.K;
+  const int HoWo = d.Ho * d.Wo;
+
+  // ---- A-load role: one pixel, 8 consecutive k per thread --------------------------------------
+  const int am = tid >> 1, akh = (tid & 1) * 8;
+  const int a_m = m0 + am;
+  const bool a_valid = a_m < M;
+  int a_n = 0, a_ih0 = 0, a_iw0 = 0;
+  if (a_valid) {
+    a_n = a_m / HoWo;
+    int rem = a_m - a_n * HoWo;
+    int oh = rem / d.Wo, ow = rem - oh * d.Wo;
+    a_ih0 = oh * d.stride - d.pad;
+    a_iw0 = ow * d.stride - d.pad;
+  }
+  // ---- B-load role: one k row, 4 consecutive couts ------------------------------------------------
+  const int bk = tid >> 4, bn4 = (tid & 15) * 4;
+  const bool b_ncol_ok = (n0 + bn4) < d.cout_pad;
+
+  float ra[8];
+  float4 rb;
+
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ra[i] = 0.f;
+    if (VEC) {
+      int kg = k0 + akh;                       // Cin % 16 == 0: the 16-k tile sits inside one tap
+      int tap = kg / d.Cin, c = kg - tap * d.Cin;
+      int r = tap / d.kw, s = tap - r * d.kw;
+      int ih = a_ih0 + r, iw = a_iw0 + s;
+      if (a_valid && (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W) {
+        const TIn* p = static_cast<const TIn*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.in_cpitch + d.in_coff + c;
+        load8(p, ra);
+        if (d.pre_scale) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ra[i] = fmaxf(fmaf(ra[i], __ldg(d.pre_scale + c + i), __ldg(d.pre_shift + c + i)), 0.f);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int kg = k0 + akh + i;
+        if (a_valid && kg < K) {
+          int tap = kg / d.Cin, c = kg - tap * d.Cin;
+          int r = tap / d.kw, s = tap - r * d.kw;
+          int ih = a_ih0 + r, iw = a_iw0 + s;
+          if ((unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W) {
+            float v;
+            if (args.in_layout == IN_NCHW_F32) {
+              v = __ldg(static_cast<const float*>(d.in) + ((size_t)(a_n * d.Cin + c) * d.H + ih) * d.W + iw);
+            } else if (args.in_layout == IN_NHWC_U8) {
+              v = (float)__ldg(static_cast<const unsigned char*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.Cin + c) / 255.f;
+            } else {
+              v = ld_as_float(static_cast<const TIn*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.in_cpitch + d.in_coff + c);
+            }
+            if (d.pre_scale) v = fmaxf(fmaf(v, __ldg(d.pre_scale + c), __ldg(d.pre_shift + c)), 0.f);
+            ra[i] = v;
+          }
+        }
+      }
+    }
+    rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b_ncol_ok && (k0 + bk) < K)
+      rb = __ldg(reinterpret_cast<const float4*>(d.w_f32 + (size_t)(k0 + bk) * d.cout_pad + n0 + bn4));
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) As[buf][akh + i][am] = ra[i];
+    *reinterpret_cast<float4*>(&Bs[buf][bk][bn4]) = rb;
+  };
+
+  const int tm = tid >> 4, tn = tid & 15;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nk = (K + BK - 1) / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tn * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue -----------------------------------------------------------------------------------
+  const int nb = n0 + tn * 4;
+  if (nb >= d.Cout) return;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bool ok = nb + j < d.Cout;
+    sc[j] = ok && d.scale ? __ldg(d.scale + nb + j) : 1.f;
+    sh[j] = ok && d.shift ? __ldg(d.shift + nb + j) : 0.f;
+  }
+  const bool full4 = nb + 3 < d.Cout;
+  const bool vec_out = full4 && !d.out_nchw && ((d.out_cpitch | d.out_coff) & 3) == 0;
+  const bool vec_res = full4 && d.res && ((d.res_cpitch | d.res_coff) & 3) == 0;
+  TOut* out = static_cast<TOut*>(d.out);
+  const TOut* res = static_cast<const TOut*>(d.res);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + tm * 8 + i;
+    if (m >= M) break;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float y = fmaf(acc[i][j], sc[j], sh[j]);
+      if (d.act == ACT_LEAKY) y = y > 0.f ? y : 0.1f * y;
+      else if (d.act == ACT_RELU) y = fmaxf(y, 0.f);
+      v[j] = y;
+    }
+    if (res) {
+      const TOut* rp = res + (size_t)m * d.res_cpitch + d.res_coff + nb;
+      if (vec_res) {
+        float r4[4];
+        load4(rp, r4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += r4[j];
+      } else {
+        for (int j = 0; j < 4 && nb + j < d.Cout; ++j) v[j] += ld_as_float(rp + j);
+      }
+    }
+    if (d.out_nchw) {
+      int n = m / HoWo, rem = m - n * HoWo;
+      for (int j = 0; j < 4 && nb + j < d.Cout; ++j)
+        store1(out + ((size_t)n * d.Cout + nb + j) * HoWo + rem, v[j]);
+    } else if (d.upsample2) {
+      int n = m / HoWo, rem = m - n * HoWo;
+      int oh = rem / d.Wo, ow = rem - oh * d.Wo;
+      const int W2 = 2 * d.Wo;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        size_t pix = ((size_t)n * 2 * d.Ho + 2 * oh + (q >> 1)) * W2 + 2 * ow + (q & 1);
+        TOut* op = out + pix * d.out_cpitch + d.out_coff + nb;
+        if (vec_out) store4(op, v);
+        else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1(op + j, v[j]);
+      }
+    } else {
+      TOut* op = out + (size_t)m * d.out_cpitch + d.out_coff + nb;
+      if (vec_out) store4(op, v);
+      else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1(op + j, v[j]);
+    }
+  }
+}
+
+template <typename TIn, typename TOut>
+static void launch_t(const ConvKArgs& a, bool vec, dim3 grid, cudaStream_t st) {
+  if (vec) conv_simt_kernel<TIn, TOut, true><<<grid, NT, 0, st>>>(a);
+  else conv_simt_kernel<TIn, TOut, false><<<grid, NT, 0, st>>>(a);
+}
+
+int launch_conv_simt(const ConvDesc& d, int in_layout, cudaStream_t st) {
+  ConvKArgs a;
+  a.d = d;
+  a.in_layout = in_layout;
+  a.M = d.N * d.Ho * d.Wo;
+  a.K = d.kh * d.kw * d.Cin;
+  if (a.M <= 0 || d.Cout <= 0) return fail(YOLO_E_SHAPE, "conv: empty problem M=%d Cout=%d", a.M, d.Cout);
+  if (d.out_nchw && d.out_dtype != DT_F32) return fail(YOLO_E_BADARG, "conv: NCHW output is fp32 only");
+  const int in_align = d.in_dtype == DT_BF16 ? 8 : 4;
+  bool vec = in_layout == IN_NHWC && d.Cin % 16 == 0 && d.in_cpitch % in_align == 0 && d.in_coff % in_align == 0 &&
+             (reinterpret_cast<uintptr_t>(d.in) & 15) == 0;
+  dim3 grid((a.M + BM - 1) / BM, (d.Cout + BN - 1) / BN);
+  const bool ib = d.in_dtype == DT_BF16 && in_layout == IN_NHWC, ob = d.out_dtype == DT_BF16;
+  if (!ib && !ob) launch_t<float, float>(a, vec, grid, st);
+  else if (!ib && ob) launch_t<float, __nv_bfloat16>(a, vec, grid, st);
+  else if (ib && !ob) launch_t<__nv_bfloat16, float>(a, vec, grid, st);
+  else launch_t<__nv_bfloat16, __nv_bfloat16>(a, vec, grid, st);
+  ++g_launches;
+  YB_CUDA(cudaGetLastError());
+  return YOLO_OK;
+}
+
+// ---- pooling (NHWC, channel-contiguous threads) -------------------------------------------------------
+template <typename T, bool IS_MAX>
+__global__ void pool_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C, int in_cpitch,
+                            int in_coff, int out_cpitch, int out_coff, int Ho, int Wo, int k, int stride, int pad) {
+  size_t total = (size_t)N * Ho * Wo * C;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C);
+    size_t pix = idx / C;
+    int ow = (int)(pix % Wo);
+    size_t t = pix / Wo;
+    int oh = (int)(t % Ho), n = (int)(t / Ho);
+    float acc = IS_MAX ? -CUDART_INF_F : 0.f;
+    for (int r = 0; r < k; ++r) {
+      int ih = oh * stride - pad + r;
+      if ((unsigned)ih >= (unsigned)H) continue;
+      for (int s = 0; s < k; ++s) {
+        int iw = ow * stride - pad + s;
+        if ((unsigned)iw >= (unsigned)W) continue;
+        float v = ld_as_float(in + ((size_t)(n * H + ih) * W + iw) * in_cpitch + in_coff + c);
+        acc = IS_MAX ? fmaxf(acc, v) : acc + v;
+      }
+    }
+    if (!IS_MAX) acc = acc / (float)(k * k);     // gluon AvgPool2D: count_include_pad, no padding used here
+    store1(out + pix * out_cpitch + out_coff + c, acc);
+  }
+}
+
+int launch_pool(const void* in, void* out, int dtype, int N, int H, int W, int C, int in_cpitch, int in_coff,
+                int out_cpitch, int out_coff, int k, int stride, int pad, int is_max, cudaStream_t st) {
+  int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  size_t total = (size_t)N * Ho * Wo * C;
+  if (total == 0) return fail(YOLO_E_SHAPE, "pool: empty problem");
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+#define YB_POOL(T, MX)                                                                                              \
+  pool_kernel<T, MX><<<blocks, 256, 0, st>>>(static_cast<const T*>(in), static_cast<T*>(out), N, H, W, C, in_cpitch, \
+                                             in_coff, out_cpitch, out_coff, Ho, Wo, k, stride, pad)
+  if (dtype == DT_F32) { if (is_max) YB_POOL(float, true); else YB_POOL(float, false); }
+  else { if (is_max) YB_POOL(__nv_bfloat16, true); else YB_POOL(__nv_bfloat16, false); }
+#undef YB_POOL
+  ++g_launches;
+  YB_CUDA(cudaGetLastError());
+  return YOLO_OK;
+}
+
+}  // namespace yb

@@ -1,0 +1,27 @@
+// tcgen05 (UMMA) implicit-GEMM convolution: host-side state and entry points.
+#pragma once
+#include "common.cuh"
+
+namespace yb {
+
+struct UmmaConv {
+  bool eligible = false;      // shape/precision can run on the tensor-core path
+  bool enabled = false;       // tensor maps built for the current workspace
+  int precision = 0;
+  int cout = 0, cin = 0, kh = 1, kw = 1, stride = 1, pad = 0;
+  int bn_tile = 0;            // N tile (UMMA N)
+  int bk = 64;                // K elements per pipeline stage (one 128-byte swizzle row)
+  void* w_packed = nullptr;   // device: [cout_padded][K] bf16, K-major, k = (r*kw+s)*Cin + c
+  size_t w_bytes = 0;
+  alignas(64) unsigned char map_a[128];   // CUtensorMap (im2col) for the activations
+  alignas(64) unsigned char map_b[128];   // CUtensorMap (tiled)  for the weights
+  int max_batch = 0;
+};
+
+int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int cout, int cin, int kh, int kw, int stride,
+                         int pad, int in_dtype, bool has_prologue, int out_nchw, cudaStream_t st);
+int umma_build_maps(UmmaConv& u, void* in_base, int max_batch, int H, int W, int C, int cpitch, int coff);
+int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st);
+void umma_release(UmmaConv& u);
+
+}  // namespace yb

@@ -1,0 +1,404 @@
+// Fused anchor decode + box selection for sm_100a.
+//
+// Replaces (reference, file:line): merge_and_slice car/YOLO.py:841-849, _init_syxhw :123-155 (tables are
+// recomputed from the flat index instead of being read), _yxhw_to_ltrb :552-566 and the per-image python
+// loop of predict :568-597 -- about 30 tiny MXNet kernels plus a device->host sync per image -- by ONE
+// launch.  One thread-block cluster of 8 CTAs per image: every CTA scans 1/8 of the image's boxes
+// (objectness channel only), the partial results meet in CTA 0's shared memory through DSMEM, CTA 0
+// finishes (top-1 gather, or sort + class-aware greedy NMS with warp-ballot suppression).
+//
+// Bit-exact selection: sigmoid is evaluated as the oracle defines it (correctly rounded expf, IEEE fp32
+// add and divide, no FMA contraction), ties resolve to the lowest flat index like MXNet's argmax.
+#include <cooperative_groups.h>
+#include <limits.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace yb {
+
+constexpr int kCluster = 8;        // CTAs per image
+constexpr int kThreads = 256;
+constexpr int kMaxRaw = 4096;      // raw candidates gathered per image (NMS mode)
+constexpr int kMaxCand = 1024;     // candidates entering suppression
+
+struct DecodeDev {
+  const float* head[YOLO_MAX_SCALES];
+  int boxes[YOLO_MAX_SCALES];      // cells * A per scale
+  int ws[YOLO_MAX_SCALES];         // cells per row
+  int off[YOLO_MAX_SCALES + 1];    // prefix sum of boxes
+  float step[YOLO_MAX_SCALES];
+  float anc[YOLO_MAX_SCALES][YOLO_MAX_ANCHORS][2];
+  int n_scales, A, C, total;
+  float img_h, img_w;
+};
+
+__device__ __forceinline__ float exp_cr(float x) {      // correctly rounded fp32 exp (oracle: exp32)
+  return (float)exp((double)x);
+}
+__device__ __forceinline__ float sigmoid_exact(float x) {   // oracle: sigmoid32
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, exp_cr(-x)));
+}
+
+__device__ __forceinline__ const float* row_ptr(const DecodeDev& g, int b, int j, int& s, int& local) {
+  s = 0;
+#pragma unroll
+  for (int k = 1; k < YOLO_MAX_SCALES; ++k)
+    if (k < g.n_scales && j >= g.off[k]) s = k;
+  local = j - g.off[s];
+  return g.head[s] + ((size_t)b * g.boxes[s] + local) * g.C;
+}
+
+// ltrb of flat box j, arithmetic in the reference's operation order (car/YOLO.py:552-566).
+__device__ __forceinline__ float4 box_ltrb(const DecodeDev& g, const float* row, int s, int local) {
+  int cell = local / g.A, a = local - cell * g.A;
+  int cy = cell / g.ws[s], cx = cell - cy * g.ws[s];
+  float st = g.step[s];
+  float y0 = (float)cy * st, x0 = (float)cx * st;
+  float by = __fdiv_rn(__fadd_rn(__fmul_rn(sigmoid_exact(row[1]), st), y0), g.img_h);
+  float bx = __fdiv_rn(__fadd_rn(__fmul_rn(sigmoid_exact(row[2]), st), x0), g.img_w);
+  float bh = __fmul_rn(exp_cr(row[3]), g.anc[s][a][0]);
+  float bw = __fmul_rn(exp_cr(row[4]), g.anc[s][a][1]);
+  float bh2 = __fmul_rn(bh, 0.5f), bw2 = __fmul_rn(bw, 0.5f);
+  return make_float4(__fsub_rn(bx, bw2), __fsub_rn(by, bh2), __fadd_rn(bx, bw2), __fadd_rn(by, bh2));
+}
+
+// yolo_gluon.get_iou (yolo_modules/yolo_gluon.py:158-167) in ltrb form, fp32 without contraction.
+__device__ __forceinline__ float iou_ltrb(float4 a, float4 b) {
+  float il = fmaxf(a.x, b.x), it = fmaxf(a.y, b.y), ir = fminf(a.z, b.z), ib = fminf(a.w, b.w);
+  float iw = fmaxf(__fsub_rn(ir, il), 0.f), ih = fmaxf(__fsub_rn(ib, it), 0.f);
+  float inter = __fmul_rn(iw, ih);
+  float aa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  float ab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+}
+
+__device__ __forceinline__ void better(float& v, int& i, float ov, int oi) {
+  if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+
+// Writes one output row in predict()'s format from the gathered head row.
+__device__ __forceinline__ void write_row(const DecodeDev& g, const float* row, float score, float4 box,
+                                          float* out, int tid, int nthreads) {
+  for (int c = tid; c < g.C; c += nthreads) {
+    float v;
+    if (c == 0) v = score;
+    else if (c == 1) v = __fmul_rn(__fadd_rn(box.y, box.w), 0.5f);   // y = (t+b)/2
+    else if (c == 2) v = __fmul_rn(__fadd_rn(box.x, box.z), 0.5f);   // x = (l+r)/2
+    else if (c == 3) v = __fsub_rn(box.w, box.y);                    // h = b-t
+    else if (c == 4) v = __fsub_rn(box.z, box.x);                    // w = r-l
+    else v = row[c];
+    out[c] = v;
+  }
+}
+
+struct NmsDev {
+  float score_thr, iou_thr;
+  int max_out, max_cand;
+};
+
+struct NmsSmem {
+  unsigned long long keys[kMaxRaw];
+  float4 box[kMaxCand];
+  int cls[kMaxCand];
+  int keep[kMaxCand];
+  unsigned alive[kMaxCand / 32];
+};
+
+template <int MODE>   // 0 = top-1 (reference semantics), 1 = NMS extension
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
+decode_kernel(const __grid_constant__ DecodeDev g, const NmsDev np, float* __restrict__ out_rows,
+              int* __restrict__ out_idx, int* __restrict__ out_count) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  __shared__ float s_wv[kThreads / 32];
+  __shared__ int s_wi[kThreads / 32];
+  __shared__ float s_cv[kCluster];      // valid in rank 0: per-CTA partial maxima
+  __shared__ int s_ci[kCluster];
+  __shared__ int s_count;               // valid in rank 0: raw candidate count (NMS)
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  NmsSmem* ns = reinterpret_cast<NmsSmem*>(dyn_smem);
+
+  if (MODE == 1) {
+    if (tid == 0) s_count = 0;
+    cluster.sync();                     // rank 0's counter is zero before anybody appends
+  }
+  int* r0_count = MODE == 1 ? cluster.map_shared_rank(&s_count, 0) : nullptr;
+  unsigned long long* r0_keys = MODE == 1 ? cluster.map_shared_rank(ns->keys, 0) : nullptr;
+
+  // ---- scan: objectness of this CTA's slice of the image ------------------------------------
+  const int per = (g.total + kCluster - 1) / kCluster;
+  const int j0 = rank * per, j1 = min(g.total, j0 + per);
+  float best = -1.f;
+  int bidx = INT_MAX;
+  for (int j = j0 + tid; j < j1; j += kThreads) {
+    int s, local;
+    const float* row = row_ptr(g, b, j, s, local);
+    float sc = sigmoid_exact(__ldg(row));
+    if (sc > best) { best = sc; bidx = j; }
+    if (MODE == 1 && sc > np.score_thr) {
+      int slot = atomicAdd(r0_count, 1);
+      if (slot < kMaxRaw)
+        r0_keys[slot] = ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(sc)) << 32) | (unsigned)j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    better(best, bidx, ov, oi);
+  }
+  if (lane == 0) { s_wv[warp] = best; s_wi[warp] = bidx; }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < kThreads / 32 ? s_wv[lane] : -1.f;
+    bidx = lane < kThreads / 32 ? s_wi[lane] : INT_MAX;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      better(best, bidx, ov, oi);
+    }
+    if (lane == 0) {
+      *cluster.map_shared_rank(&s_cv[rank], 0) = best;
+      *cluster.map_shared_rank(&s_ci[rank], 0) = bidx;
+    }
+  }
+  cluster.sync();                       // partials (and candidates) have landed in rank 0
+  if (rank != 0) return;
+
+  // ---- rank 0: final top-1 ---------------------------------------------------------------------
+  best = lane < kCluster ? s_cv[lane] : -1.f;
+  bidx = lane < kCluster ? s_ci[lane] : INT_MAX;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    better(best, bidx, ov, oi);
+  }
+  best = __shfl_sync(0xffffffffu, best, 0);
+  bidx = __shfl_sync(0xffffffffu, bidx, 0);
+  if (bidx == INT_MAX) bidx = 0;        // all-NaN objectness: defined as index 0
+
+  if (MODE == 0) {
+    int s, local;
+    const float* row = row_ptr(g, b, bidx, s, local);
+    float4 box = box_ltrb(g, row, s, local);
+    write_row(g, row, sigmoid_exact(row[0]), box, out_rows + (size_t)b * g.C, tid, kThreads);
+    if (tid == 0) out_idx[b] = bidx;
+    return;
+  }
+
+  // ---- rank 0: NMS -------------------------------------------------------------------------------
+  int raw = s_count;
+  if (raw > kMaxRaw) {                  // cannot order more than kMaxRaw candidates exactly
+    if (tid == 0) out_count[b] = -raw;
+    return;
+  }
+  if (raw == 0) {                       // nothing above the threshold: keep the top-1 alone
+    if (tid == 0)
+      ns->keys[0] = ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(best)) << 32) | (unsigned)bidx;
+    raw = 1;
+  }
+  int P = 1;
+  while (P < raw) P <<= 1;
+  for (int i = raw + tid; i < P; i += kThreads) ns->keys[i] = ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {    // bitonic sort: (score desc, index asc)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += kThreads) {
+        int x = i ^ j;
+        if (x > i) {
+          unsigned long long a = ns->keys[i], c = ns->keys[x];
+          bool up = (i & k) == 0;
+          if ((a > c) == up) { ns->keys[i] = c; ns->keys[x] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int K = min(raw, min(np.max_cand, kMaxCand));
+  for (int i = tid; i < K; i += kThreads) {
+    int j = (int)(ns->keys[i] & 0xFFFFFFFFu);
+    int s, local;
+    const float* row = row_ptr(g, b, j, s, local);
+    ns->box[i] = box_ltrb(g, row, s, local);
+    int c = 0;
+    float cv = -CUDART_INF_F;
+    for (int q = 6; q < g.C; ++q) {     // np.argmax over class logits: first maximum
+      float v = row[q];
+      if (v > cv) { cv = v; c = q - 6; }
+    }
+    ns->cls[i] = c;
+  }
+  for (int i = tid; i < kMaxCand / 32; i += kThreads) {
+    int lo = i * 32;
+    ns->alive[i] = lo + 32 <= K ? 0xFFFFFFFFu : (lo >= K ? 0u : ((1u << (K - lo)) - 1u));
+  }
+  __syncthreads();
+  int nk = 0;
+  const int nblk = (K + 31) / 32;
+  for (int i = 0; i < K; ++i) {
+    if (!((ns->alive[i >> 5] >> (i & 31)) & 1u)) continue;      // block-uniform
+    if (tid == 0) ns->keep[nk] = i;
+    ++nk;
+    if (nk >= np.max_out) break;
+    float4 bi = ns->box[i];
+    int ci = ns->cls[i];
+    for (int blk = (i >> 5) + warp; blk < nblk; blk += kThreads / 32) {
+      int j = blk * 32 + lane;
+      bool sup = j > i && j < K && ns->cls[j] == ci && iou_ltrb(bi, ns->box[j]) > np.iou_thr;
+      unsigned m = __ballot_sync(0xffffffffu, sup);
+      if (lane == 0 && m) ns->alive[blk] &= ~m;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int k = warp; k < nk; k += kThreads / 32) {
+    int i = ns->keep[k];
+    unsigned long long key = ns->keys[i];
+    int j = (int)(key & 0xFFFFFFFFu);
+    float sc = __uint_as_float(0xFFFFFFFFu - (unsigned)(key >> 32));
+    int s, local;
+    const float* row = row_ptr(g, b, j, s, local);
+    write_row(g, row, sc, ns->box[i], out_rows + ((size_t)b * np.max_out + k) * g.C, lane, 32);
+    if (lane == 0) out_idx[(size_t)b * np.max_out + k] = j;
+  }
+  if (tid == 0) out_count[b] = nk;
+}
+
+// ---- licence-plate pose decode ---------------------------------------------------------------
+// mode 0: car_and_LP/YOLO.py:133-169 (NHWC map, argmax of sigmoid(score), 7 outputs)
+// mode 1: licence_plate/LP_detection.py:147-162 (NCHW map, argmax of the raw score, ch outputs)
+__global__ void __launch_bounds__(kThreads)
+decode_lp_kernel(const float* __restrict__ lp, int n, int ch, int mode, float r0, float r1, float r2,
+                 float* __restrict__ out_rows, int* __restrict__ out_idx) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* base = lp + (size_t)b * n * ch;
+  const size_t cell_stride = mode == 0 ? ch : 1, ch_stride = mode == 0 ? 1 : n;
+  __shared__ float s_wv[kThreads / 32];
+  __shared__ int s_wi[kThreads / 32];
+  float best = -CUDART_INF_F;
+  int bidx = INT_MAX;
+  for (int j = tid; j < n; j += kThreads) {
+    float v = __ldg(base + j * cell_stride);
+    if (mode == 0) v = sigmoid_exact(v);
+    if (v > best) { best = v; bidx = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    better(best, bidx, ov, oi);
+  }
+  if (lane == 0) { s_wv[warp] = best; s_wi[warp] = bidx; }
+  __syncthreads();
+  if (warp != 0) return;
+  best = lane < kThreads / 32 ? s_wv[lane] : -CUDART_INF_F;
+  bidx = lane < kThreads / 32 ? s_wi[lane] : INT_MAX;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    better(best, bidx, ov, oi);
+  }
+  bidx = __shfl_sync(0xffffffffu, bidx, 0);
+  if (bidx == INT_MAX) bidx = 0;
+  const int nout = mode == 0 ? 7 : ch;
+  if (lane < nout) {
+    float v = base[bidx * cell_stride + lane * ch_stride];
+    float o;
+    if (lane == 0) o = sigmoid_exact(v);
+    else if (lane < 4) o = __fmul_rn(v, 1000.f);
+    else if (lane < 7) {
+      float rm = lane == 4 ? r0 : (lane == 5 ? r1 : r2);
+      float d = __fmul_rn(__fmul_rn(__fsub_rn(sigmoid_exact(v), 0.5f), 2.f), rm);
+      o = __fdiv_rn(__fmul_rn(d, 3.14159274101257324f), 180.f);
+    } else o = v;
+    out_rows[(size_t)b * nout + lane] = o;
+  }
+  if (lane == 0 && out_idx) out_idx[b] = bidx;
+}
+
+static int make_dev(const yolo_decode_geom* g, const void* const* heads, DecodeDev& d) {
+  if (!g || !heads) return fail(YOLO_E_BADARG, "decode: null geometry or heads");
+  if (g->n_scales < 1 || g->n_scales > YOLO_MAX_SCALES || g->n_anchors < 1 || g->n_anchors > YOLO_MAX_ANCHORS)
+    return fail(YOLO_E_BADARG, "decode: n_scales=%d n_anchors=%d out of range", g->n_scales, g->n_anchors);
+  if (g->channels_per_anchor < 6) return fail(YOLO_E_BADARG, "decode: channels_per_anchor=%d < 6", g->channels_per_anchor);
+  d.n_scales = g->n_scales; d.A = g->n_anchors; d.C = g->channels_per_anchor;
+  d.img_h = (float)g->height; d.img_w = (float)g->width;
+  d.off[0] = 0;
+  for (int s = 0; s < g->n_scales; ++s) {
+    if (g->step[s] <= 0 || g->height % g->step[s] || g->width % g->step[s])
+      return fail(YOLO_E_SHAPE, "decode: size %dx%d not divisible by step %d", g->height, g->width, g->step[s]);
+    if (!heads[s]) return fail(YOLO_E_BADARG, "decode: heads[%d] is null", s);
+    d.head[s] = static_cast<const float*>(heads[s]);
+    d.ws[s] = g->width / g->step[s];
+    d.boxes[s] = (g->height / g->step[s]) * d.ws[s] * g->n_anchors;
+    d.off[s + 1] = d.off[s] + d.boxes[s];
+    d.step[s] = (float)g->step[s];
+    for (int a = 0; a < g->n_anchors; ++a) { d.anc[s][a][0] = g->anchors[s][a][0]; d.anc[s][a][1] = g->anchors[s][a][1]; }
+  }
+  for (int s = g->n_scales; s < YOLO_MAX_SCALES; ++s) { d.head[s] = nullptr; d.boxes[s] = 0; d.ws[s] = 1; d.off[s + 1] = d.off[s]; d.step[s] = 1.f; }
+  d.total = d.off[g->n_scales];
+  return YOLO_OK;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" int yolo_decode_top1(const yolo_decode_geom* g, const void* const* heads, int batch,
+                                float* out_rows, int32_t* out_idx, void* stream) {
+  DecodeDev d;
+  int rc = make_dev(g, heads, d);
+  if (rc) return rc;
+  if (batch < 0 || !out_rows || !out_idx) return fail(YOLO_E_BADARG, "decode_top1: bad batch/outputs");
+  if (batch == 0) return YOLO_OK;
+  NmsDev np{0.f, 0.f, 0, 0};
+  dim3 grid(kCluster, batch);
+  decode_kernel<0><<<grid, kThreads, 0, (cudaStream_t)stream>>>(d, np, out_rows, out_idx, nullptr);
+  ++g_launches;
+  YB_CUDA(cudaGetLastError());
+  return YOLO_OK;
+}
+
+extern "C" int yolo_decode_nms(const yolo_decode_geom* g, const void* const* heads, int batch,
+                               const yolo_nms_params* p, float* out_rows, int32_t* out_idx, int32_t* out_count,
+                               void* stream) {
+  DecodeDev d;
+  int rc = make_dev(g, heads, d);
+  if (rc) return rc;
+  if (!p || batch < 0 || !out_rows || !out_idx || !out_count) return fail(YOLO_E_BADARG, "decode_nms: bad arguments");
+  if (p->max_out < 1 || p->max_cand < 1 || p->max_cand > kMaxCand || p->max_out > p->max_cand)
+    return fail(YOLO_E_BADARG, "decode_nms: need 1 <= max_out <= max_cand <= %d", kMaxCand);
+  if (batch == 0) return YOLO_OK;
+  NmsDev np{p->score_thr, p->iou_thr, p->max_out, p->max_cand};
+  static bool attr_set = false;
+  if (!attr_set) {
+    YB_CUDA(cudaFuncSetAttribute(decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem)));
+    attr_set = true;
+  }
+  dim3 grid(kCluster, batch);
+  decode_kernel<1><<<grid, kThreads, sizeof(NmsSmem), (cudaStream_t)stream>>>(d, np, out_rows, out_idx, out_count);
+  ++g_launches;
+  YB_CUDA(cudaGetLastError());
+  return YOLO_OK;
+}
+
+extern "C" int yolo_decode_lp(const void* lp, int batch, int hs, int ws, int ch, int mode, const float r_max[3],
+                              float* out_rows, int32_t* out_idx, void* stream) {
+  if (!lp || !r_max || !out_rows || batch < 0 || hs < 1 || ws < 1) return fail(YOLO_E_BADARG, "decode_lp: bad arguments");
+  if (ch < 7 || ch > 32 || (mode != 0 && mode != 1)) return fail(YOLO_E_BADARG, "decode_lp: ch=%d mode=%d unsupported", ch, mode);
+  if (batch == 0) return YOLO_OK;
+  decode_lp_kernel<<<batch, kThreads, 0, (cudaStream_t)stream>>>(static_cast<const float*>(lp), hs * ws, ch, mode,
+                                                               r_max[0], r_max[1], r_max[2], out_rows, out_idx);
+  ++g_launches;
+  YB_CUDA(cudaGetLastError());
+  return YOLO_OK;
+}

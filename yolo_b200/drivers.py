@@ -1,0 +1,151 @@
+"""Host-side mirrors of the reference's task drivers for the hot path (same names, arguments and
+return values, so callers such as car/video_node.py keep working):
+
+  * ``YOLO``                    car/YOLO.py:48-110, predict :568-597
+  * ``CarLPYOLO``               car_and_LP/YOLO.py:98-169 (class ``YOLO`` there), predict_LP :133-157
+  * ``LicencePlateDetectioin``  licence_plate/LP_detection.py:100-162 (spelling is the reference's)
+
+Only the hot path lives here (construction from spec.yaml, ``net.forward``, ``predict`` / ``predict_LP``);
+rendering, ROS, tensorboard and checkpoint rotation are out of scope.
+There is no CPU fallback: unlike ``yolo_gluon.get_ctx`` (yolo_modules/yolo_gluon.py:393-396) a missing GPU
+raises.
+"""
+from __future__ import annotations
+
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import yaml
+
+from . import api
+
+
+def get_ctx(gpu):
+    """yolo_gluon.get_ctx (yolo_modules/yolo_gluon.py:380-408): list of device indices; no CPU fallback."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("NO GPU be Detected! yolo_b200 has no CPU fallback")
+    if isinstance(gpu, str):
+        gpu = [g for g in gpu.replace(" ", "").split(",") if g != ""]
+    ctx = [int(g) for g in gpu if int(g) < torch.cuda.device_count()]
+    if not ctx:
+        raise RuntimeError(f"GPU index error: {gpu}")
+    return ctx
+
+
+def _load_spec(args, spec):
+    if spec is None:
+        with open(os.path.join(args.version, "spec.yaml")) as f:
+            spec = yaml.safe_load(f)
+    return spec
+
+
+def _args(args, **kw):
+    if args is None:
+        args = SimpleNamespace(version=None, mode="video", gpu="0", weight=None, record=0, trt=0)
+    for k, v in kw.items():
+        if not hasattr(args, k):
+            setattr(args, k, v)
+    return args
+
+
+class YOLO:
+    """Vehicle box + azimuth detector (car/YOLO.py).  ``params`` is a dict name -> fp32 array in the
+    canonical naming of the C library (``net.param_shapes()``); without it the net must be loaded later
+    through ``self.net.load_params``."""
+
+    net_type = "carnet"
+
+    def __init__(self, args=None, spec=None, params=None, precision="fp32", max_batch=1):
+        args = _args(args, gpu="0", mode="video")
+        self.ctx = get_ctx(args.gpu)
+        spec = _load_spec(args, spec)
+        for key in spec:                                   # car/YOLO.py:58-59
+            setattr(self, key, spec[key])
+        self.spec = spec
+        self.all_anchors = np.asarray(self.all_anchors, np.float32)
+        self.num_class = len(self.classes) if hasattr(self, "classes") else self.slice_point[-1] - 6
+        if self.slice_point[-1] != 6 + self.num_class:
+            raise ValueError("slice_point[-1] must equal 6 + len(classes)")
+        self._init_step()
+        self._init_area()
+        self.version = getattr(args, "version", None)
+        self.precision, self.max_batch = precision, max_batch
+        self._init_net(spec, params)
+
+    def _init_step(self):                                  # car/YOLO.py:112-116
+        self.steps = api.init_steps(self.spec)
+
+    def _init_area(self):                                  # car/YOLO.py:118-121
+        h, w = self.size
+        self.area = [int(h * w / step ** 2) for step in self.steps]
+
+    def _init_net(self, spec, params):                     # car/YOLO.py:91-110
+        self.net = api.Net(self.net_type, spec, self.precision, self.max_batch, self.ctx[0])
+        if params is not None:
+            self.net.load_params(params)
+
+    # -------------------- Validation Part -------------------- #
+    def predict(self, batch_out, mode="top1", score_thr=0.5, iou_thr=0.45, max_out=100, max_cand=1024, return_index=False):
+        """car/YOLO.py:568-597: list of (B,HW_s,A,C) heads -> np.float32 (B, 6+num_class)
+        rows [score, y, x, h, w, rotate, class logits...].  ``mode='nms'`` is the north-star extension and
+        returns (rows (B,max_out,C), indices (B,max_out), counts (B,)) as numpy arrays."""
+        heads = list(batch_out)[: len(self.steps)]
+        if mode == "top1":
+            rows, idx = api.decode_top1(self.spec, heads, self.steps)
+            if return_index:
+                both = torch.cat([rows, idx.view(torch.float32).view(-1, 1)], dim=1)   # one D2H like asnumpy(); bit-cast
+                both = both.cpu().numpy()
+                return both[:, :-1].copy(), np.ascontiguousarray(both[:, -1]).view(np.int32)
+            return rows.cpu().numpy()
+        if mode == "nms":
+            rows, idx, cnt = api.decode_nms(self.spec, heads, score_thr, iou_thr, max_out, max_cand, self.steps)
+            return rows.cpu().numpy(), idx.cpu().numpy(), cnt.cpu().numpy()
+        raise ValueError("mode must be 'top1' or 'nms'")
+
+
+class CarLPYOLO(YOLO):
+    """car_and_LP/YOLO.py ``YOLO``: CarLPNet + predict_LP."""
+
+    net_type = "carlpnet"
+
+    def predict_LP(self, LP_batch_out, return_index=False):
+        """car_and_LP/YOLO.py:133-157: [LP_x (B,Hs,Ws,10)] -> np.float32 (B,7)."""
+        lp = LP_batch_out[0] if isinstance(LP_batch_out, (list, tuple)) else LP_batch_out
+        rows, idx = api.decode_lp(lp, 0, self.LP_r_max)
+        if return_index:
+            return rows.cpu().numpy(), idx.cpu().numpy()
+        return rows.cpu().numpy()
+
+
+class LicencePlateDetectioin:
+    """licence_plate/LP_detection.py: DenseNet pose detector."""
+
+    def __init__(self, args=None, spec=None, params=None, precision="fp32", max_batch=1):
+        args = _args(args, gpu="0", mode="video")
+        spec = _load_spec(args, spec)
+        for key in spec:                                   # LP_detection.py:106-107
+            setattr(self, key, spec[key])
+        self.spec = spec
+        self.version = getattr(args, "version", None)
+        self.ctx = get_ctx(args.gpu)
+        self.num_downsample = len(self.block_config) + 1
+        self.net = api.Net("lpdensenet", spec, precision, max_batch, self.ctx[0])
+        if params is not None:
+            self.net.load_params(params)
+
+    def predict_LP(self, batch_out, return_index=False):
+        """LP_detection.py:147-162: NCHW (B,10,H,W) net output -> (10,) for image 0 (argmax of the raw score)."""
+        out = batch_out[0] if isinstance(batch_out, (list, tuple)) else batch_out
+        rows, idx = api.decode_lp(out, 1, self.LP_r_max)
+        rows = rows.cpu().numpy()
+        if return_index:
+            return rows[0], int(idx[0].item())
+        return rows[0]
+
+    def predict_LP_batch(self, batch_out):
+        """Same decode applied to every image of the batch -> (B,10) (extension for batched serving)."""
+        out = batch_out[0] if isinstance(batch_out, (list, tuple)) else batch_out
+        rows, _ = api.decode_lp(out, 1, self.LP_r_max)
+        return rows.cpu().numpy()
