@@ -32,13 +32,15 @@ f32 = np.float32
 
 def sigmoid32(x):
     x = np.asarray(x, dtype=np.float32)
-    e = np.exp(-x.astype(np.float64)).astype(np.float32)       # correctly rounded expf(-x)
+    with np.errstate(over="ignore"):
+        e = np.exp(-x.astype(np.float64)).astype(np.float32)   # correctly rounded expf(-x); +inf on overflow like expf
     return (f32(1.0) / (f32(1.0) + e)).astype(np.float32)
 
 
 def exp32(x):
     x = np.asarray(x, dtype=np.float32)
-    return np.exp(x.astype(np.float64)).astype(np.float32)
+    with np.errstate(over="ignore"):
+        return np.exp(x.astype(np.float64)).astype(np.float32)
 
 
 def init_steps(spec):

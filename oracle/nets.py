@@ -282,10 +282,24 @@ def spec_tiny(size=(64, 96), C=9, lp=False):
     return s
 
 
+def spec_micro(size=(64, 64), C=8, lp=False):
+    """Very small spec whose parameters fit in a committed fixture (tests/golden)."""
+    s = dict(size=list(size), layers=[1, 1, 1, 1, 1], channels=[4, 8, 8, 16, 16, 32],
+             slice_point=[1, 3, 5, 6, C], all_anchors=V1_ANCHORS, use_fp16=False)
+    if lp:
+        s.update(LP_slice_point=[1, 3, 4, 7, 10], LP_r_max=[45, 60, 45], LP_num_class=3)
+    return s
+
+
 def spec_lp_v2():
     """licence_plate/v2/spec.yaml:1-10."""
     return dict(size=[320, 512], LP_slice_point=[1, 3, 4, 7, 10], LP_r_max=[45, 60, 45], LP_num_class=3,
                 num_init_features=64, growth_rate=16, block_config=[6, 12, 24, 16])
+
+
+def spec_lp_micro():
+    return dict(size=[64, 64], LP_slice_point=[1, 3, 4, 7, 10], LP_r_max=[45, 60, 45], LP_num_class=3,
+                num_init_features=8, growth_rate=4, block_config=[2, 2, 2, 2])
 
 
 def spec_lp_tiny():

@@ -1,0 +1,40 @@
+"""Helpers shared by the GPU parity tests (the oracle is the checker, never the thing measured)."""
+import numpy as np
+import torch
+
+from oracle import decode, nets, weights
+
+F64_CACHE = {}
+
+
+def oracle_outputs(net, spec, params, x, dtype=torch.float32):
+    """Flat list of oracle outputs as numpy (heads..., [lp]) or [out] for the DenseNet."""
+    tp = {k: torch.from_numpy(np.asarray(v)).to(dtype) for k, v in params.items()}
+    with torch.no_grad():
+        out = nets.forward(net, spec, tp, torch.from_numpy(x).to(dtype))
+    if net == "carnet":
+        return [h.numpy() for h in out]
+    if net == "carlpnet":
+        return [h.numpy() for h in out[0]] + [out[1][0].numpy()]
+    return [out.numpy()]
+
+
+def noise_aware_check(got, ref32, ref64, floor=1e-4, factor=4.0, what=""):
+    """|got - fp64 truth| must be within max(floor, factor x the fp32 oracle's own distance to fp64).
+
+    The reference computes in fp32, so the oracle's fp32 rounding noise (measured against its own fp64
+    evaluation) is the resolution at which 'matches the reference' is defined; floor = the north-star
+    tolerance 1e-4."""
+    got, ref32, ref64 = np.asarray(got, np.float64), np.asarray(ref32, np.float64), np.asarray(ref64, np.float64)
+    noise = float(np.abs(ref32 - ref64).max())
+    err = float(np.abs(got - ref64).max())
+    tol = max(floor, factor * noise)
+    assert err <= tol, f"{what}: |cuda-f64|={err:.3e} > tol={tol:.3e} (oracle fp32 noise {noise:.3e}, |cuda-f32oracle|={np.abs(got-ref32).max():.3e})"
+    return err, noise
+
+
+def cuda_net(net, spec, params, precision="fp32", max_batch=2):
+    import yolo_b200
+    n = yolo_b200.Net(net, spec, precision=precision, max_batch=max_batch)
+    n.load_params(params)
+    return n
