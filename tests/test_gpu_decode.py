@@ -91,7 +91,8 @@ def test_top1_full_size_property():
 
 @pytest.mark.parametrize("spec,B,thr,iou,max_out,max_cand", [
     (nets.spec_micro(size=(64, 96), C=10), 3, 0.05, 0.3, 16, 256),
-    (nets.spec_dk53(), 3, 0.02, 0.45, 100, 1024),
+    (nets.spec_dk53(), 3, 0.3, 0.45, 100, 1024),
+    (nets.spec_dk53(), 2, 0.1, 0.45, 50, 1024),            # ~1900 raw candidates -> truncated to max_cand after the sort
     (nets.spec_dk53(), 2, 0.2, 0.1, 8, 64),
     (nets.spec_v1_native(), 2, 0.9999, 0.5, 10, 100),      # nothing passes -> top-1 alone
 ])

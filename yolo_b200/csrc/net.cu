@@ -369,8 +369,8 @@ extern "C" int yolo_create(const yolo_spec* spec, int device, yolo_handle** out)
   if (!spec || !out) return fail(YOLO_E_BADARG, "create: null spec/out");
   *out = nullptr;
   if (spec->max_batch < 1) return fail(YOLO_E_BADARG, "create: max_batch=%d", spec->max_batch);
-  if (spec->precision < YOLO_PREC_FP32 || spec->precision > YOLO_PREC_TF32X3) return fail(YOLO_E_BADARG, "create: precision=%d", spec->precision);
-  if (spec->precision == YOLO_PREC_TF32X3) return fail(YOLO_E_UNSUPPORTED, "create: YOLO_PREC_TF32X3 is not implemented yet");
+  if (spec->precision < YOLO_PREC_FP32 || spec->precision > YOLO_PREC_BF16X6) return fail(YOLO_E_BADARG, "create: precision=%d", spec->precision);
+  if (spec->precision == YOLO_PREC_BF16X6) return fail(YOLO_E_UNSUPPORTED, "create: YOLO_PREC_BF16X6 is not implemented yet");
   std::unique_ptr<yolo_handle> h(new yolo_handle());
   h->spec = *spec;
   h->device = device;
