@@ -54,6 +54,9 @@ extern "C" {
 #define YOLO_NET_CARNET      0   /* BasicYOLONet topology + CarNet forward */
 #define YOLO_NET_CARLPNET    1   /* CarNet + licence-plate pose branch */
 #define YOLO_NET_LPDENSENET  2   /* DenseNet licence-plate detector */
+#define YOLO_NET_DEBUGCONV   3   /* kernel unit-test harness: conv "pre" (3 -> channels[0], 3x3) then conv "test"
+                                    (channels[0] -> channels[1], k=layers[0], stride=layers[1], pad=layers[2],
+                                    act=layers[3], residual=layers[4], bn=layers[5]); output fp32 NHWC */
 
 /* precision: arithmetic of the convolution path */
 #define YOLO_PREC_FP32    0   /* fp32 FFMA implicit GEMM (parity grade)            */

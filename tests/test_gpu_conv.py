@@ -1,0 +1,74 @@
+"""Kernel-level parity of the convolution kernels (FFMA and tcgen05) on single layers, through the C ABI's
+YOLO_NET_DEBUGCONV harness: every shape class of the networks (1x1, 3x3 s1/s2, 13x13 maps, Cout=90 heads,
+ragged M tails, residual add) against a float64 evaluation of the same layer on the harness's own input."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+LEAKY, RELU = 1, 2
+
+
+def run_layer(precision, B, H, W, cin, cout, k, stride, pad, act=LEAKY, residual=0, bn=1, seed=0):
+    import yolo_b200
+    rng = np.random.default_rng(seed)
+    spec = dict(size=[H, W], cin=cin, cout=cout, k=k, stride=stride, pad=pad, act=act, residual=residual, bn=bn)
+    net = yolo_b200.Net("debugconv", spec, precision=precision, max_batch=B)
+    params = {}
+    for name, shape in net.param_shapes():
+        leaf = name.rsplit(".", 1)[1]
+        if leaf == "weight":
+            fan_in = shape[1] * shape[2] * shape[3]
+            params[name] = (rng.standard_normal(shape) / np.sqrt(fan_in)).astype(np.float32)
+        elif leaf in ("gamma", "running_var"):
+            params[name] = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+        else:
+            params[name] = rng.normal(0, 0.3, shape).astype(np.float32)
+    net.load_params(params)
+    x = rng.uniform(0, 1, size=(B, 3, H, W)).astype(np.float32)
+    out = net.forward(data=torch.from_numpy(x).cuda())[0].asnumpy()           # (B, Ho, Wo, C) fp32
+    pre = net.activation("pre", (B, cin, H, W))                                # exact value of the layer input
+    if residual:
+        Ho, Wo = H, W
+        out = net.activation("test", (B, cout, Ho, Wo)).transpose(0, 2, 3, 1)
+    t = torch.from_numpy(pre).double()
+    y = F.conv2d(t, torch.from_numpy(params["test.weight"]).double(), None, stride, pad)
+    if bn:
+        g, b, m, v = (torch.from_numpy(params["test." + n]).double() for n in ("gamma", "beta", "running_mean", "running_var"))
+        y = (y - m[None, :, None, None]) / torch.sqrt(v[None, :, None, None] + 1e-5) * g[None, :, None, None] + b[None, :, None, None]
+    else:
+        y = y + torch.from_numpy(params["test.bias"]).double()[None, :, None, None]
+    if act == LEAKY:
+        y = F.leaky_relu(y, 0.1)
+    elif act == RELU:
+        y = F.relu(y)
+    if residual:
+        y = y + t
+    return out, y.permute(0, 2, 3, 1).numpy(), net
+
+
+SHAPES = [
+    # B, H, W, cin, cout, k, stride, pad, act, residual, bn
+    (2, 13, 13, 64, 128, 3, 1, 1, LEAKY, 0, 1),        # odd map, ragged M tail (338 pixels)
+    (3, 26, 26, 128, 64, 1, 1, 0, LEAKY, 0, 1),        # 1x1
+    (2, 32, 48, 64, 128, 3, 2, 1, LEAKY, 0, 1),        # stride-2 down conv
+    (1, 16, 16, 256, 90, 1, 1, 0, 0, 0, 0),            # head: Cout=90, bias, linear
+    (2, 20, 20, 128, 128, 3, 1, 1, LEAKY, 1, 1),       # residual block tail
+    (1, 8, 8, 512, 1024, 3, 1, 1, LEAKY, 0, 1),        # deep K = 4608, several N tiles
+    (5, 7, 9, 64, 32, 1, 1, 0, LEAKY, 0, 1),           # tiny Cout, M = 315
+    (1, 12, 12, 32, 64, 3, 1, 1, LEAKY, 0, 1),         # Cin % 64 != 0 -> FFMA kernel in every precision
+    (2, 10, 10, 192, 48, 3, 1, 1, RELU, 0, 1),
+]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16x6", 2e-5), ("bf16", 6e-2)])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_single_layer(shape, precision, tol):
+    B, H, W, cin, cout, k, s, p, act, res, bn = shape
+    out, ref, net = run_layer(precision, B, H, W, cin, cout, k, s, p, act, res, bn, seed=hash(shape) % 1000)
+    assert out.shape == ref.shape
+    err = np.abs(out - ref)
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert err.max() <= tol * scale, f"{precision} {shape}: max err {err.max():.3e} (scale {scale:.2f}), mean {err.mean():.3e}"

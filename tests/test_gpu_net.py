@@ -14,7 +14,7 @@ from oracle import decode, nets, weights
 
 pytestmark = pytest.mark.gpu
 
-PARITY_PRECISIONS = ["fp32"]
+PARITY_PRECISIONS = ["fp32", "bf16x6"]     # both are fp32-grade; bf16x6 runs on the tcgen05 tensor cores
 
 
 def _run(net, spec, params, x, precision, u8=None):
@@ -123,7 +123,9 @@ def test_dk53_416_end_to_end(precision):
     pred, idx = y.predict(out, return_index=True)
     opred, oidx = decode.predict(spec, ref32, return_index=True)
     np.testing.assert_array_equal(idx, oidx)
-    np.testing.assert_allclose(pred[:, :5], opred[:, :5], rtol=0, atol=1e-4)     # score + bbox
+    pred64 = decode.predict(spec, [r.astype(np.float32) for r in ref64])         # rows decoded from the fp64 heads
+    assert np.abs(pred[:, :4] - opred[:, :4]).max() <= 1e-4                      # score, y, x, h vs the fp32 oracle
+    noise_aware_check(pred[:, :5], opred[:, :5], pred64[:, :5], what="dk53 score+bbox")   # w = exp(tw)*anchor > 1 amplifies
     sm = lambda z: np.exp(z - z.max(-1, keepdims=True)) / np.exp(z - z.max(-1, keepdims=True)).sum(-1, keepdims=True)
     np.testing.assert_allclose(sm(pred[:, 6:]), sm(opred[:, 6:]), rtol=0, atol=1e-4)   # class scores (video_node.py:246)
     # the one-call host path gives the same rows
@@ -131,6 +133,19 @@ def test_dk53_416_end_to_end(precision):
     np.testing.assert_array_equal(idx2, oidx)
     np.testing.assert_allclose(rows, pred, rtol=0, atol=1e-6)
     assert abs(y.net.conv_flops_per_image / 1e9 - 113.263) < 1e-2
+
+
+def test_bf16_fast_mode_reported_tolerance():
+    """Single-pass bf16 (tcgen05) is the fast mode: NOT parity grade.  With synthetic (non-contractive) weights its
+    error is measured and bounded loosely here; structural bugs (wrong tap / swizzle / plane) would be O(1-10)."""
+    spec = nets.spec_tiny(size=(128, 128), C=30)
+    params = weights.make_params("carnet", spec, seed=5, calib_batch=4)
+    x, _ = weights.synthetic_frames(2, spec["size"], seed=77)
+    n, res = _run("carnet", spec, params, x, "bf16")
+    ref32 = oracle_outputs("carnet", spec, params, x)
+    for a, r in zip(res, ref32):
+        err = np.abs(a - r.reshape(a.shape))
+        assert err.mean() < 0.08 and err.max() < 1.0, (err.mean(), err.max())
 
 
 def test_batch_limits_and_errors():

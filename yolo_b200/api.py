@@ -14,9 +14,9 @@ import torch
 
 from . import _lib
 from ._lib import (DecodeGeom, NmsParams, YoloSpec, check, IN_NCHW_F32, IN_NHWC_U8, NET_CARNET, NET_CARLPNET,
-                   NET_LPDENSENET, PRECISIONS)
+                   NET_LPDENSENET, NET_DEBUGCONV, PRECISIONS)
 
-NET_TYPES = {"carnet": NET_CARNET, "carlpnet": NET_CARLPNET, "lpdensenet": NET_LPDENSENET}
+NET_TYPES = {"carnet": NET_CARNET, "carlpnet": NET_CARLPNET, "lpdensenet": NET_LPDENSENET, "debugconv": NET_DEBUGCONV}
 
 
 def _require_cuda():
@@ -94,6 +94,10 @@ def make_c_spec(net_type, spec, precision="fp32", max_batch=1):
         for i in range(3):
             s.lp_r_max[i] = float(spec["LP_r_max"][i])
         s.lp_num_class = int(spec["LP_num_class"])
+    if net_type == "debugconv":          # kernel unit-test harness (see include/yolo_b200.h)
+        s.channels[0], s.channels[1] = int(spec["cin"]), int(spec["cout"])
+        for i, key in enumerate(("k", "stride", "pad", "act", "residual", "bn")):
+            s.layers[i] = int(spec[key])
     if net_type == "lpdensenet":
         s.num_init_features, s.growth_rate = int(spec["num_init_features"]), int(spec["growth_rate"])
         cfg = spec["block_config"]

@@ -26,14 +26,15 @@ int fail(int code, const char* fmt, ...);
 extern thread_local int g_launches;
 
 enum Act : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
-enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+// DT_BF16X3: three bf16 planes v = v0 + v1 + v2 (exact split of an fp32 value), plane p at element offset p*plane_stride
+enum DType : int { DT_F32 = 0, DT_BF16 = 1, DT_BF16X3 = 2 };
 
 // One convolution (+ fused prologue / epilogue) as executed by the kernels.  Activations are NHWC;
 // a tensor may be a channel slice [coff, coff+C) of a wider buffer with `cpitch` channels per pixel
 // (this is how route concat and DenseNet concat are realised without copies).
 struct ConvDesc {
   // input
-  const void* in;  int in_dtype;  int N, H, W, Cin;  int in_cpitch, in_coff;
+  const void* in;  int in_dtype;  int N, H, W, Cin;  int in_cpitch, in_coff;  long long in_plane_stride;
   // filter
   int kh, kw, stride, pad;  int Cout;
   const float* w_f32;          // [kh*kw*Cin][CoutPad4] fp32 (SIMT path), k = (r*kw+s)*Cin + c
@@ -42,9 +43,9 @@ struct ConvDesc {
   const float* pre_scale;  const float* pre_shift;
   // epilogue: y = act(acc*scale[o] + shift[o]) (+ residual)
   const float* scale;  const float* shift;  int act;
-  const void* res;  int res_cpitch, res_coff;   // same dtype as out
+  const void* res;  int res_cpitch, res_coff;  long long res_plane_stride;   // same dtype as out
   // output
-  void* out;  int out_dtype;  int Ho, Wo;  int out_cpitch, out_coff;
+  void* out;  int out_dtype;  int Ho, Wo;  int out_cpitch, out_coff;  long long out_plane_stride;
   int upsample2;               // write every output pixel to the 2x2 block of a (2Ho, 2Wo) map
   int out_nchw;                // fp32 only: store as (N, Cout, Ho, Wo)
 };
@@ -52,6 +53,7 @@ struct ConvDesc {
 // in_layout: 0 = NHWC of in_dtype, 1 = NCHW fp32 (stem only), 2 = NHWC uint8 scaled by 1/255 (stem only)
 int launch_conv_simt(const ConvDesc& d, int in_layout, cudaStream_t st);
 int launch_pool(const void* in, void* out, int dtype, int N, int H, int W, int C, int in_cpitch, int in_coff,
-                int out_cpitch, int out_coff, int k, int stride, int pad, int is_max, cudaStream_t st);
+                long long in_plane_stride, int out_cpitch, int out_coff, long long out_plane_stride, int k, int stride, int pad,
+                int is_max, cudaStream_t st);
 
 }  // namespace yb

@@ -72,7 +72,63 @@ __device__ __forceinline__ void load4(const __nv_bfloat16* p, float v[4]) {
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
-template <typename TIn, typename TOut, bool VEC>
+// ---- plane-aware accessors: NP == 3 is the exact three-way bf16 split (DT_BF16X3) -----------------------
+template <int NP, typename T>
+__device__ __forceinline__ void load8p(const T* p, long long ps, float v[8]) {
+  load8(p, v);
+  if (NP == 3) {
+    float t[8];
+    load8(p + ps, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += t[i];
+    load8(p + 2 * ps, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += t[i];
+  }
+}
+template <int NP, typename T>
+__device__ __forceinline__ void load4p(const T* p, long long ps, float v[4]) {
+  load4(p, v);
+  if (NP == 3) {
+    float t[4];
+    load4(p + ps, t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += t[i];
+    load4(p + 2 * ps, t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += t[i];
+  }
+}
+template <int NP, typename T>
+__device__ __forceinline__ float ld1p(const T* p, long long ps) {
+  float v = ld_as_float(p);
+  if (NP == 3) { v += ld_as_float(p + ps); v += ld_as_float(p + 2 * ps); }
+  return v;
+}
+template <int NP, typename T>
+__device__ __forceinline__ void store4p(T* p, long long ps, const float v[4]) {
+  if (NP == 1) { store4(p, v); return; }
+  float r[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+  for (int pl = 0; pl < 3; ++pl) {
+    float h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h[i] = __bfloat162float(__float2bfloat16_rn(r[i])); r[i] -= h[i]; }
+    store4(p + pl * ps, h);
+  }
+}
+template <int NP, typename T>
+__device__ __forceinline__ void store1p(T* p, long long ps, float v) {
+  if (NP == 1) { store1(p, v); return; }
+#pragma unroll
+  for (int pl = 0; pl < 3; ++pl) {
+    float h = __bfloat162float(__float2bfloat16_rn(v));
+    store1(p + pl * ps, h);
+    v -= h;
+  }
+}
+
+template <typename TIn, int NPI, typename TOut, int NPO, bool VEC>
 __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ ConvKArgs args) {
   const ConvDesc& d = args.d;
   __shared__ __align__(16) float As[2][BK][AS_PITCH];
@@ -112,7 +168,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
       int ih = a_ih0 + r, iw = a_iw0 + s;
       if (a_valid && (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W) {
         const TIn* p = static_cast<const TIn*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.in_cpitch + d.in_coff + c;
-        load8(p, ra);
+        load8p<NPI>(p, d.in_plane_stride, ra);
         if (d.pre_scale) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) ra[i] = fmaxf(fmaf(ra[i], __ldg(d.pre_scale + c + i), __ldg(d.pre_shift + c + i)), 0.f);
@@ -133,7 +189,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
             } else if (args.in_layout == IN_NHWC_U8) {
               v = (float)__ldg(static_cast<const unsigned char*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.Cin + c) / 255.f;
             } else {
-              v = ld_as_float(static_cast<const TIn*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.in_cpitch + d.in_coff + c);
+              v = ld1p<NPI>(static_cast<const TIn*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.in_cpitch + d.in_coff + c, d.in_plane_stride);
             }
             if (d.pre_scale) v = fmaxf(fmaf(v, __ldg(d.pre_scale + c), __ldg(d.pre_shift + c)), 0.f);
             ra[i] = v;
@@ -214,17 +270,17 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
       const TOut* rp = res + (size_t)m * d.res_cpitch + d.res_coff + nb;
       if (vec_res) {
         float r4[4];
-        load4(rp, r4);
+        load4p<NPO>(rp, d.res_plane_stride, r4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] += r4[j];
       } else {
-        for (int j = 0; j < 4 && nb + j < d.Cout; ++j) v[j] += ld_as_float(rp + j);
+        for (int j = 0; j < 4 && nb + j < d.Cout; ++j) v[j] += ld1p<NPO>(rp + j, d.res_plane_stride);
       }
     }
     if (d.out_nchw) {
       int n = m / HoWo, rem = m - n * HoWo;
       for (int j = 0; j < 4 && nb + j < d.Cout; ++j)
-        store1(out + ((size_t)n * d.Cout + nb + j) * HoWo + rem, v[j]);
+        store1p<NPO>(out + ((size_t)n * d.Cout + nb + j) * HoWo + rem, d.out_plane_stride, v[j]);
     } else if (d.upsample2) {
       int n = m / HoWo, rem = m - n * HoWo;
       int oh = rem / d.Wo, ow = rem - oh * d.Wo;
@@ -233,21 +289,21 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
       for (int q = 0; q < 4; ++q) {
         size_t pix = ((size_t)n * 2 * d.Ho + 2 * oh + (q >> 1)) * W2 + 2 * ow + (q & 1);
         TOut* op = out + pix * d.out_cpitch + d.out_coff + nb;
-        if (vec_out) store4(op, v);
-        else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1(op + j, v[j]);
+        if (vec_out) store4p<NPO>(op, d.out_plane_stride, v);
+        else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1p<NPO>(op + j, d.out_plane_stride, v[j]);
       }
     } else {
       TOut* op = out + (size_t)m * d.out_cpitch + d.out_coff + nb;
-      if (vec_out) store4(op, v);
-      else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1(op + j, v[j]);
+      if (vec_out) store4p<NPO>(op, d.out_plane_stride, v);
+      else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1p<NPO>(op + j, d.out_plane_stride, v[j]);
     }
   }
 }
 
-template <typename TIn, typename TOut>
+template <typename TIn, int NPI, typename TOut, int NPO>
 static void launch_t(const ConvKArgs& a, bool vec, dim3 grid, cudaStream_t st) {
-  if (vec) conv_simt_kernel<TIn, TOut, true><<<grid, NT, 0, st>>>(a);
-  else conv_simt_kernel<TIn, TOut, false><<<grid, NT, 0, st>>>(a);
+  if (vec) conv_simt_kernel<TIn, NPI, TOut, NPO, true><<<grid, NT, 0, st>>>(a);
+  else conv_simt_kernel<TIn, NPI, TOut, NPO, false><<<grid, NT, 0, st>>>(a);
 }
 
 int launch_conv_simt(const ConvDesc& d, int in_layout, cudaStream_t st) {
@@ -258,24 +314,31 @@ int launch_conv_simt(const ConvDesc& d, int in_layout, cudaStream_t st) {
   a.K = d.kh * d.kw * d.Cin;
   if (a.M <= 0 || d.Cout <= 0) return fail(YOLO_E_SHAPE, "conv: empty problem M=%d Cout=%d", a.M, d.Cout);
   if (d.out_nchw && d.out_dtype != DT_F32) return fail(YOLO_E_BADARG, "conv: NCHW output is fp32 only");
-  const int in_align = d.in_dtype == DT_BF16 ? 8 : 4;
+  const int idt = in_layout == IN_NHWC ? d.in_dtype : DT_F32;
+  const int in_align = idt == DT_F32 ? 4 : 8;
   bool vec = in_layout == IN_NHWC && d.Cin % 16 == 0 && d.in_cpitch % in_align == 0 && d.in_coff % in_align == 0 &&
-             (reinterpret_cast<uintptr_t>(d.in) & 15) == 0;
+             (reinterpret_cast<uintptr_t>(d.in) & 15) == 0 && (idt != DT_BF16X3 || d.in_plane_stride % 8 == 0);
   dim3 grid((a.M + BM - 1) / BM, (d.Cout + BN - 1) / BN);
-  const bool ib = d.in_dtype == DT_BF16 && in_layout == IN_NHWC, ob = d.out_dtype == DT_BF16;
-  if (!ib && !ob) launch_t<float, float>(a, vec, grid, st);
-  else if (!ib && ob) launch_t<float, __nv_bfloat16>(a, vec, grid, st);
-  else if (ib && !ob) launch_t<__nv_bfloat16, float>(a, vec, grid, st);
-  else launch_t<__nv_bfloat16, __nv_bfloat16>(a, vec, grid, st);
+  using bf = __nv_bfloat16;
+  const int odt = d.out_dtype;
+  if (idt == DT_F32 && odt == DT_F32) launch_t<float, 1, float, 1>(a, vec, grid, st);
+  else if (idt == DT_F32 && odt == DT_BF16) launch_t<float, 1, bf, 1>(a, vec, grid, st);
+  else if (idt == DT_F32 && odt == DT_BF16X3) launch_t<float, 1, bf, 3>(a, vec, grid, st);
+  else if (idt == DT_BF16 && odt == DT_BF16) launch_t<bf, 1, bf, 1>(a, vec, grid, st);
+  else if (idt == DT_BF16 && odt == DT_F32) launch_t<bf, 1, float, 1>(a, vec, grid, st);
+  else if (idt == DT_BF16X3 && odt == DT_BF16X3) launch_t<bf, 3, bf, 3>(a, vec, grid, st);
+  else if (idt == DT_BF16X3 && odt == DT_F32) launch_t<bf, 3, float, 1>(a, vec, grid, st);
+  else return fail(YOLO_E_UNSUPPORTED, "conv: dtype combination in=%d out=%d", idt, odt);
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
 }
 
 // ---- pooling (NHWC, channel-contiguous threads) -------------------------------------------------------
-template <typename T, bool IS_MAX>
+template <typename T, int NP, bool IS_MAX>
 __global__ void pool_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C, int in_cpitch,
-                            int in_coff, int out_cpitch, int out_coff, int Ho, int Wo, int k, int stride, int pad) {
+                            int in_coff, long long in_ps, int out_cpitch, int out_coff, long long out_ps, int Ho, int Wo, int k,
+                            int stride, int pad) {
   size_t total = (size_t)N * Ho * Wo * C;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     int c = (int)(idx % C);
@@ -290,27 +353,29 @@ __global__ void pool_kernel(const T* __restrict__ in, T* __restrict__ out, int N
       for (int s = 0; s < k; ++s) {
         int iw = ow * stride - pad + s;
         if ((unsigned)iw >= (unsigned)W) continue;
-        float v = ld_as_float(in + ((size_t)(n * H + ih) * W + iw) * in_cpitch + in_coff + c);
+        float v = ld1p<NP>(in + ((size_t)(n * H + ih) * W + iw) * in_cpitch + in_coff + c, in_ps);
         acc = IS_MAX ? fmaxf(acc, v) : acc + v;
       }
     }
     if (!IS_MAX) acc = acc / (float)(k * k);     // gluon AvgPool2D: count_include_pad, no padding used here
-    store1(out + pix * out_cpitch + out_coff + c, acc);
+    store1p<NP>(out + pix * out_cpitch + out_coff + c, out_ps, acc);
   }
 }
 
 int launch_pool(const void* in, void* out, int dtype, int N, int H, int W, int C, int in_cpitch, int in_coff,
-                int out_cpitch, int out_coff, int k, int stride, int pad, int is_max, cudaStream_t st) {
+                long long in_plane_stride, int out_cpitch, int out_coff, long long out_plane_stride, int k, int stride, int pad,
+                int is_max, cudaStream_t st) {
   int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   size_t total = (size_t)N * Ho * Wo * C;
   if (total == 0) return fail(YOLO_E_SHAPE, "pool: empty problem");
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-#define YB_POOL(T, MX)                                                                                              \
-  pool_kernel<T, MX><<<blocks, 256, 0, st>>>(static_cast<const T*>(in), static_cast<T*>(out), N, H, W, C, in_cpitch, \
-                                             in_coff, out_cpitch, out_coff, Ho, Wo, k, stride, pad)
-  if (dtype == DT_F32) { if (is_max) YB_POOL(float, true); else YB_POOL(float, false); }
-  else { if (is_max) YB_POOL(__nv_bfloat16, true); else YB_POOL(__nv_bfloat16, false); }
+#define YB_POOL(T, NP, MX)                                                                                              \
+  pool_kernel<T, NP, MX><<<blocks, 256, 0, st>>>(static_cast<const T*>(in), static_cast<T*>(out), N, H, W, C, in_cpitch, \
+                                                 in_coff, in_plane_stride, out_cpitch, out_coff, out_plane_stride, Ho, Wo, k, stride, pad)
+  if (dtype == DT_F32) { if (is_max) YB_POOL(float, 1, true); else YB_POOL(float, 1, false); }
+  else if (dtype == DT_BF16) { if (is_max) YB_POOL(__nv_bfloat16, 1, true); else YB_POOL(__nv_bfloat16, 1, false); }
+  else { if (is_max) YB_POOL(__nv_bfloat16, 3, true); else YB_POOL(__nv_bfloat16, 3, false); }
 #undef YB_POOL
   ++g_launches;
   YB_CUDA(cudaGetLastError());
