@@ -61,7 +61,8 @@ extern "C" {
 /* precision: arithmetic of the convolution path */
 #define YOLO_PREC_FP32    0   /* fp32 FFMA implicit GEMM (parity grade)            */
 #define YOLO_PREC_BF16    1   /* bf16 operands, fp32 accumulate, tcgen05 tensor cores */
-#define YOLO_PREC_BF16X6  2   /* fp32 emulated by 6 bf16 tcgen05 passes on 3-way split operands */
+#define YOLO_PREC_BF16X6  2   /* fp32 emulated by 6 bf16 tcgen05 passes on 3-way split operands (24-bit operands) */
+#define YOLO_PREC_FP16X3  3   /* fp32 emulated by 3 fp16 tcgen05 passes on 2-way split operands (22-bit operands) */
 
 /* input layouts accepted by yolo_forward */
 #define YOLO_IN_NCHW_F32  0   /* (B,3,H,W) fp32 in [0,1] - what cv_img_2_ndarray produces */

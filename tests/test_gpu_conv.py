@@ -60,10 +60,13 @@ SHAPES = [
     (5, 7, 9, 64, 32, 1, 1, 0, LEAKY, 0, 1),           # tiny Cout, M = 315
     (1, 12, 12, 32, 64, 3, 1, 1, LEAKY, 0, 1),         # Cin % 64 != 0 -> FFMA kernel in every precision
     (2, 10, 10, 192, 48, 3, 1, 1, RELU, 0, 1),
+    (2, 24, 24, 96, 64, 3, 2, 1, LEAKY, 0, 1),         # Cin % 64 == 32 -> 64-byte swizzle rows (BLOCK_K = 32)
+    (1, 16, 16, 32, 32, 1, 1, 0, LEAKY, 1, 1),         # 1x1 residual, BLOCK_K = 32
+    (1, 9, 9, 16, 24, 3, 1, 1, LEAKY, 0, 1),           # FFMA kernel in every precision
 ]
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16x6", 2e-5), ("bf16", 6e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("fp16x3", 1e-5), ("bf16x6", 1e-5), ("bf16", 6e-2)])
 @pytest.mark.parametrize("shape", SHAPES)
 def test_single_layer(shape, precision, tol):
     B, H, W, cin, cout, k, s, p, act, res, bn = shape

@@ -14,7 +14,7 @@ from oracle import decode, nets, weights
 
 pytestmark = pytest.mark.gpu
 
-PARITY_PRECISIONS = ["fp32", "bf16x6"]     # both are fp32-grade; bf16x6 runs on the tcgen05 tensor cores
+PARITY_PRECISIONS = ["fp32", "fp16x3", "bf16x6"]     # all fp32-grade; fp16x3 / bf16x6 run on the tcgen05 tensor cores
 
 
 def _run(net, spec, params, x, precision, u8=None):

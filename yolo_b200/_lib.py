@@ -13,9 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libyolo_b200.so")
 
 MAX_STAGES, MAX_SCALES, MAX_ANCHORS, MAX_BLOCKS = 8, 3, 8, 8
 NET_CARNET, NET_CARLPNET, NET_LPDENSENET, NET_DEBUGCONV = 0, 1, 2, 3
-PREC_FP32, PREC_BF16, PREC_BF16X6 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_BF16X6, PREC_FP16X3 = 0, 1, 2, 3
 IN_NCHW_F32, IN_NHWC_U8 = 0, 1
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x6": PREC_BF16X6}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x6": PREC_BF16X6, "fp16x3": PREC_FP16X3}
 
 
 class YoloSpec(C.Structure):

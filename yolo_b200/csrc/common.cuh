@@ -27,7 +27,11 @@ extern thread_local int g_launches;
 
 enum Act : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
 // DT_BF16X3: three bf16 planes v = v0 + v1 + v2 (exact split of an fp32 value), plane p at element offset p*plane_stride
-enum DType : int { DT_F32 = 0, DT_BF16 = 1, DT_BF16X3 = 2 };
+// DT_F16X2:  two fp16 planes  v = v0 + v1 * 2^-11 (22-bit split; v1 is stored pre-scaled by 2^11 to stay normal in fp16)
+enum DType : int { DT_F32 = 0, DT_BF16 = 1, DT_BF16X3 = 2, DT_F16X2 = 3 };
+constexpr float kF16LoScale = 2048.f, kF16LoScaleInv = 1.f / 2048.f, kF16Max = 65504.f;
+inline int dtype_planes(int dt) { return dt == DT_BF16X3 ? 3 : (dt == DT_F16X2 ? 2 : 1); }
+inline int dtype_bytes_per_elem(int dt) { return dt == DT_F32 ? 4 : 2 * dtype_planes(dt); }
 
 // One convolution (+ fused prologue / epilogue) as executed by the kernels.  Activations are NHWC;
 // a tensor may be a channel slice [coff, coff+C) of a wider buffer with `cpitch` channels per pixel
@@ -52,6 +56,8 @@ struct ConvDesc {
 
 // in_layout: 0 = NHWC of in_dtype, 1 = NCHW fp32 (stem only), 2 = NHWC uint8 scaled by 1/255 (stem only)
 int launch_conv_simt(const ConvDesc& d, int in_layout, cudaStream_t st);
+bool stem_eligible(const ConvDesc& d, int in_layout);          // dedicated 3x3 kernel for the 3-channel network input
+int launch_stem(const ConvDesc& d, int in_layout, cudaStream_t st);
 int launch_pool(const void* in, void* out, int dtype, int N, int H, int W, int C, int in_cpitch, int in_coff,
                 long long in_plane_stride, int out_cpitch, int out_coff, long long out_plane_stride, int k, int stride, int pad,
                 int is_max, cudaStream_t st);

@@ -14,6 +14,7 @@
 // GEMM view: M = N*Ho*Wo output pixels, N = Cout, K = kh*kw*Cin with k = (r*kw + s)*Cin + c.
 // CTA tile 128(M) x 64(N) x 16(K), 256 threads, 8x4 accumulators per thread, register-staged
 // double buffering of the shared-memory tiles.
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -72,64 +73,107 @@ __device__ __forceinline__ void load4(const __nv_bfloat16* p, float v[4]) {
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
-// ---- plane-aware accessors: NP == 3 is the exact three-way bf16 split (DT_BF16X3) -----------------------
-template <int NP, typename T>
-__device__ __forceinline__ void load8p(const T* p, long long ps, float v[8]) {
+__device__ __forceinline__ float ld_as_float(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void load8(const __half* p, float v[8]) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load4(const __half* p, float v[4]) {
+  uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+  float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4(__half* p, const float v[4]) {
+  __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<unsigned*>(&a);
+  u.y = *reinterpret_cast<unsigned*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ void store1(__half* p, float v) { *p = __float2half_rn(v); }
+
+// ---- storage formats ---------------------------------------------------------------------------------------
+// F32 / BF16: one plane.  BF16X3: v = p0 + p1 + p2 (exact 24-bit split).  F16X2: v = p0 + p1 * 2^-11 (22-bit split);
+// plane q lives at element offset q * plane_stride.
+struct FmtF32 { using T = float; static constexpr int NP = 1; static constexpr int ALIGN = 4; };
+struct FmtBF16 { using T = __nv_bfloat16; static constexpr int NP = 1; static constexpr int ALIGN = 8; };
+struct FmtBF16X3 { using T = __nv_bfloat16; static constexpr int NP = 3; static constexpr int ALIGN = 8; };
+struct FmtF16X2 { using T = __half; static constexpr int NP = 2; static constexpr int ALIGN = 8; };
+
+template <class F> __device__ __forceinline__ float plane_weight(int q) {
+  return (F::NP == 2 && q == 1) ? kF16LoScaleInv : 1.f;
+}
+template <class F>
+__device__ __forceinline__ void load8f(const typename F::T* p, long long ps, float v[8]) {
   load8(p, v);
-  if (NP == 3) {
+#pragma unroll
+  for (int q = 1; q < F::NP; ++q) {
     float t[8];
-    load8(p + ps, t);
+    load8(p + q * ps, t);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += t[i];
-    load8(p + 2 * ps, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += t[i];
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(t[i], plane_weight<F>(q), v[i]);
   }
 }
-template <int NP, typename T>
-__device__ __forceinline__ void load4p(const T* p, long long ps, float v[4]) {
+template <class F>
+__device__ __forceinline__ void load4f(const typename F::T* p, long long ps, float v[4]) {
   load4(p, v);
-  if (NP == 3) {
+#pragma unroll
+  for (int q = 1; q < F::NP; ++q) {
     float t[4];
-    load4(p + ps, t);
+    load4(p + q * ps, t);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] += t[i];
-    load4(p + 2 * ps, t);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] += t[i];
+    for (int i = 0; i < 4; ++i) v[i] = fmaf(t[i], plane_weight<F>(q), v[i]);
   }
 }
-template <int NP, typename T>
-__device__ __forceinline__ float ld1p(const T* p, long long ps) {
+template <class F>
+__device__ __forceinline__ float ld1f(const typename F::T* p, long long ps) {
   float v = ld_as_float(p);
-  if (NP == 3) { v += ld_as_float(p + ps); v += ld_as_float(p + 2 * ps); }
+#pragma unroll
+  for (int q = 1; q < F::NP; ++q) v = fmaf(ld_as_float(p + q * ps), plane_weight<F>(q), v);
   return v;
 }
-template <int NP, typename T>
-__device__ __forceinline__ void store4p(T* p, long long ps, const float v[4]) {
-  if (NP == 1) { store4(p, v); return; }
-  float r[4] = {v[0], v[1], v[2], v[3]};
+// split one value into the planes of format F (returned as floats that are exactly representable in F::T)
+template <class F>
+__device__ __forceinline__ void split_planes(float v, float h[F::NP]) {
+  if (F::NP == 1) { h[0] = v; return; }
+  if (F::NP == 3) {
 #pragma unroll
-  for (int pl = 0; pl < 3; ++pl) {
-    float h[4];
+    for (int q = 0; q < 3; ++q) { h[q] = __bfloat162float(__float2bfloat16_rn(v)); v -= h[q]; }
+    return;
+  }
+  float c = fminf(fmaxf(v, -kF16Max), kF16Max);
+  h[0] = __half2float(__float2half_rn(c));
+  h[1 % F::NP] = fminf(fmaxf((v - h[0]) * kF16LoScale, -kF16Max), kF16Max);
+}
+template <class F>
+__device__ __forceinline__ void store4f(typename F::T* p, long long ps, const float v[4]) {
+  float h[4][F::NP];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { h[i] = __bfloat162float(__float2bfloat16_rn(r[i])); r[i] -= h[i]; }
-    store4(p + pl * ps, h);
+  for (int i = 0; i < 4; ++i) split_planes<F>(v[i], h[i]);
+#pragma unroll
+  for (int q = 0; q < F::NP; ++q) {
+    const float t[4] = {h[0][q], h[1][q], h[2][q], h[3][q]};
+    store4(p + q * ps, t);
   }
 }
-template <int NP, typename T>
-__device__ __forceinline__ void store1p(T* p, long long ps, float v) {
-  if (NP == 1) { store1(p, v); return; }
+template <class F>
+__device__ __forceinline__ void store1f(typename F::T* p, long long ps, float v) {
+  float h[F::NP];
+  split_planes<F>(v, h);
 #pragma unroll
-  for (int pl = 0; pl < 3; ++pl) {
-    float h = __bfloat162float(__float2bfloat16_rn(v));
-    store1(p + pl * ps, h);
-    v -= h;
-  }
+  for (int q = 0; q < F::NP; ++q) store1(p + q * ps, h[q]);
 }
 
-template <typename TIn, int NPI, typename TOut, int NPO, bool VEC>
+template <class FI, class FO, bool VEC>
 __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ ConvKArgs args) {
+  using TIn = typename FI::T;
+  using TOut = typename FO::T;
   const ConvDesc& d = args.d;
   __shared__ __align__(16) float As[2][BK][AS_PITCH];
   __shared__ __align__(16) float Bs[2][BK][BN];
@@ -168,7 +212,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
       int ih = a_ih0 + r, iw = a_iw0 + s;
       if (a_valid && (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W) {
         const TIn* p = static_cast<const TIn*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.in_cpitch + d.in_coff + c;
-        load8p<NPI>(p, d.in_plane_stride, ra);
+        load8f<FI>(p, d.in_plane_stride, ra);
         if (d.pre_scale) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) ra[i] = fmaxf(fmaf(ra[i], __ldg(d.pre_scale + c + i), __ldg(d.pre_shift + c + i)), 0.f);
@@ -189,7 +233,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
             } else if (args.in_layout == IN_NHWC_U8) {
               v = (float)__ldg(static_cast<const unsigned char*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.Cin + c) / 255.f;
             } else {
-              v = ld1p<NPI>(static_cast<const TIn*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.in_cpitch + d.in_coff + c, d.in_plane_stride);
+              v = ld1f<FI>(static_cast<const TIn*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.in_cpitch + d.in_coff + c, d.in_plane_stride);
             }
             if (d.pre_scale) v = fmaxf(fmaf(v, __ldg(d.pre_scale + c), __ldg(d.pre_shift + c)), 0.f);
             ra[i] = v;
@@ -270,17 +314,17 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
       const TOut* rp = res + (size_t)m * d.res_cpitch + d.res_coff + nb;
       if (vec_res) {
         float r4[4];
-        load4p<NPO>(rp, d.res_plane_stride, r4);
+        load4f<FO>(rp, d.res_plane_stride, r4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] += r4[j];
       } else {
-        for (int j = 0; j < 4 && nb + j < d.Cout; ++j) v[j] += ld1p<NPO>(rp + j, d.res_plane_stride);
+        for (int j = 0; j < 4 && nb + j < d.Cout; ++j) v[j] += ld1f<FO>(rp + j, d.res_plane_stride);
       }
     }
     if (d.out_nchw) {
       int n = m / HoWo, rem = m - n * HoWo;
       for (int j = 0; j < 4 && nb + j < d.Cout; ++j)
-        store1p<NPO>(out + ((size_t)n * d.Cout + nb + j) * HoWo + rem, d.out_plane_stride, v[j]);
+        store1f<FO>(out + ((size_t)n * d.Cout + nb + j) * HoWo + rem, d.out_plane_stride, v[j]);
     } else if (d.upsample2) {
       int n = m / HoWo, rem = m - n * HoWo;
       int oh = rem / d.Wo, ow = rem - oh * d.Wo;
@@ -289,21 +333,21 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
       for (int q = 0; q < 4; ++q) {
         size_t pix = ((size_t)n * 2 * d.Ho + 2 * oh + (q >> 1)) * W2 + 2 * ow + (q & 1);
         TOut* op = out + pix * d.out_cpitch + d.out_coff + nb;
-        if (vec_out) store4p<NPO>(op, d.out_plane_stride, v);
-        else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1p<NPO>(op + j, d.out_plane_stride, v[j]);
+        if (vec_out) store4f<FO>(op, d.out_plane_stride, v);
+        else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1f<FO>(op + j, d.out_plane_stride, v[j]);
       }
     } else {
       TOut* op = out + (size_t)m * d.out_cpitch + d.out_coff + nb;
-      if (vec_out) store4p<NPO>(op, d.out_plane_stride, v);
-      else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1p<NPO>(op + j, d.out_plane_stride, v[j]);
+      if (vec_out) store4f<FO>(op, d.out_plane_stride, v);
+      else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1f<FO>(op + j, d.out_plane_stride, v[j]);
     }
   }
 }
 
-template <typename TIn, int NPI, typename TOut, int NPO>
+template <class FI, class FO>
 static void launch_t(const ConvKArgs& a, bool vec, dim3 grid, cudaStream_t st) {
-  if (vec) conv_simt_kernel<TIn, NPI, TOut, NPO, true><<<grid, NT, 0, st>>>(a);
-  else conv_simt_kernel<TIn, NPI, TOut, NPO, false><<<grid, NT, 0, st>>>(a);
+  if (vec) conv_simt_kernel<FI, FO, true><<<grid, NT, 0, st>>>(a);
+  else conv_simt_kernel<FI, FO, false><<<grid, NT, 0, st>>>(a);
 }
 
 int launch_conv_simt(const ConvDesc& d, int in_layout, cudaStream_t st) {
@@ -317,26 +361,133 @@ int launch_conv_simt(const ConvDesc& d, int in_layout, cudaStream_t st) {
   const int idt = in_layout == IN_NHWC ? d.in_dtype : DT_F32;
   const int in_align = idt == DT_F32 ? 4 : 8;
   bool vec = in_layout == IN_NHWC && d.Cin % 16 == 0 && d.in_cpitch % in_align == 0 && d.in_coff % in_align == 0 &&
-             (reinterpret_cast<uintptr_t>(d.in) & 15) == 0 && (idt != DT_BF16X3 || d.in_plane_stride % 8 == 0);
+             (reinterpret_cast<uintptr_t>(d.in) & 15) == 0 && d.in_plane_stride % 8 == 0;
   dim3 grid((a.M + BM - 1) / BM, (d.Cout + BN - 1) / BN);
-  using bf = __nv_bfloat16;
   const int odt = d.out_dtype;
-  if (idt == DT_F32 && odt == DT_F32) launch_t<float, 1, float, 1>(a, vec, grid, st);
-  else if (idt == DT_F32 && odt == DT_BF16) launch_t<float, 1, bf, 1>(a, vec, grid, st);
-  else if (idt == DT_F32 && odt == DT_BF16X3) launch_t<float, 1, bf, 3>(a, vec, grid, st);
-  else if (idt == DT_BF16 && odt == DT_BF16) launch_t<bf, 1, bf, 1>(a, vec, grid, st);
-  else if (idt == DT_BF16 && odt == DT_F32) launch_t<bf, 1, float, 1>(a, vec, grid, st);
-  else if (idt == DT_BF16X3 && odt == DT_BF16X3) launch_t<bf, 3, bf, 3>(a, vec, grid, st);
-  else if (idt == DT_BF16X3 && odt == DT_F32) launch_t<bf, 3, float, 1>(a, vec, grid, st);
+  if (idt == DT_F32 && odt == DT_F32) launch_t<FmtF32, FmtF32>(a, vec, grid, st);
+  else if (idt == DT_F32 && odt == DT_BF16) launch_t<FmtF32, FmtBF16>(a, vec, grid, st);
+  else if (idt == DT_F32 && odt == DT_BF16X3) launch_t<FmtF32, FmtBF16X3>(a, vec, grid, st);
+  else if (idt == DT_F32 && odt == DT_F16X2) launch_t<FmtF32, FmtF16X2>(a, vec, grid, st);
+  else if (idt == DT_BF16 && odt == DT_BF16) launch_t<FmtBF16, FmtBF16>(a, vec, grid, st);
+  else if (idt == DT_BF16 && odt == DT_F32) launch_t<FmtBF16, FmtF32>(a, vec, grid, st);
+  else if (idt == DT_BF16X3 && odt == DT_BF16X3) launch_t<FmtBF16X3, FmtBF16X3>(a, vec, grid, st);
+  else if (idt == DT_BF16X3 && odt == DT_F32) launch_t<FmtBF16X3, FmtF32>(a, vec, grid, st);
+  else if (idt == DT_F16X2 && odt == DT_F16X2) launch_t<FmtF16X2, FmtF16X2>(a, vec, grid, st);
+  else if (idt == DT_F16X2 && odt == DT_F32) launch_t<FmtF16X2, FmtF32>(a, vec, grid, st);
   else return fail(YOLO_E_UNSUPPORTED, "conv: dtype combination in=%d out=%d", idt, odt);
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
 }
 
+// ---- stem: 3x3 convolution on the 3-channel network input ----------------------------------------------
+// One thread per output pixel, the 27 input taps in registers, weights broadcast from shared memory, 16 output
+// channels at a time.  Reads the reference's input contract directly - NCHW fp32 in [0,1] (cv_img_2_ndarray,
+// yolo_modules/yolo_gluon.py:335-357) or the uint8 HWC camera frame with the /255 fused - and writes the first NHWC
+// activation in the precision's storage format.  (K = 27 is too small for the tensor cores; this layer is
+// bound by its output write.)
+constexpr int STEM_CO = 16;
+template <class FO, int LAYOUT>
+__global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ ConvKArgs args) {
+  using TOut = typename FO::T;
+  const ConvDesc& d = args.d;
+  extern __shared__ float s_w[];                 // [27][cout_pad] then scale[Cout], shift[Cout]
+  const int cp = d.cout_pad;
+  for (int i = threadIdx.x; i < 27 * cp; i += blockDim.x) s_w[i] = __ldg(d.w_f32 + i);
+  float* s_sc = s_w + 27 * cp;
+  float* s_sh = s_sc + d.Cout;
+  for (int i = threadIdx.x; i < d.Cout; i += blockDim.x) {
+    s_sc[i] = d.scale ? __ldg(d.scale + i) : 1.f;
+    s_sh[i] = d.shift ? __ldg(d.shift + i) : 0.f;
+  }
+  __syncthreads();
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= args.M) return;
+  const int HoWo = d.Ho * d.Wo;
+  const int n = m / HoWo, rem = m - n * HoWo;
+  const int oh = rem / d.Wo, ow = rem - oh * d.Wo;
+  float x[27];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int ih = oh * d.stride - d.pad + r, iw = ow * d.stride - d.pad + q;
+      const bool ok = (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = 0.f;
+        if (ok) {
+          if (LAYOUT == IN_NCHW_F32) v = __ldg(static_cast<const float*>(d.in) + ((size_t)(n * 3 + c) * d.H + ih) * d.W + iw);
+          else v = (float)__ldg(static_cast<const unsigned char*>(d.in) + ((size_t)(n * d.H + ih) * d.W + iw) * 3 + c) / 255.f;
+        }
+        x[(r * 3 + q) * 3 + c] = v;
+      }
+    }
+  TOut* op = static_cast<TOut*>(d.out) + (size_t)m * d.out_cpitch + d.out_coff;
+  for (int o0 = 0; o0 < d.Cout; o0 += STEM_CO) {
+    float acc[STEM_CO];
+#pragma unroll
+    for (int j = 0; j < STEM_CO; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+#pragma unroll
+      for (int j4 = 0; j4 < STEM_CO; j4 += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(&s_w[k * cp + o0 + j4]);
+        acc[j4] = fmaf(x[k], w.x, acc[j4]);
+        acc[j4 + 1] = fmaf(x[k], w.y, acc[j4 + 1]);
+        acc[j4 + 2] = fmaf(x[k], w.z, acc[j4 + 2]);
+        acc[j4 + 3] = fmaf(x[k], w.w, acc[j4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < STEM_CO; j4 += 4) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y = fmaf(acc[j4 + j], s_sc[o0 + j4 + j], s_sh[o0 + j4 + j]);
+        if (d.act == ACT_LEAKY) y = y > 0.f ? y : 0.1f * y;
+        else if (d.act == ACT_RELU) y = fmaxf(y, 0.f);
+        v[j] = y;
+      }
+      store4f<FO>(op + o0 + j4, d.out_plane_stride, v);
+    }
+  }
+}
+
+template <class FO>
+static void launch_stem_t(const ConvKArgs& a, int in_layout, int smem, cudaStream_t st) {
+  const int blocks = (a.M + 255) / 256;
+  if (in_layout == IN_NCHW_F32) stem3x3_kernel<FO, IN_NCHW_F32><<<blocks, 256, smem, st>>>(a);
+  else stem3x3_kernel<FO, IN_NHWC_U8><<<blocks, 256, smem, st>>>(a);
+}
+
+bool stem_eligible(const ConvDesc& d, int in_layout) {
+  return (in_layout == IN_NCHW_F32 || in_layout == IN_NHWC_U8) && d.Cin == 3 && d.kh == 3 && d.kw == 3 && d.Cout % STEM_CO == 0 &&
+         d.Cout <= 128 && !d.res && !d.pre_scale && !d.upsample2 && !d.out_nchw && ((d.out_cpitch | d.out_coff) & 7) == 0 &&
+         d.cout_pad == d.Cout;
+}
+
+int launch_stem(const ConvDesc& d, int in_layout, cudaStream_t st) {
+  ConvKArgs a;
+  a.d = d;
+  a.in_layout = in_layout;
+  a.M = d.N * d.Ho * d.Wo;
+  a.K = 27;
+  const int smem = (27 * d.cout_pad + 2 * d.Cout) * 4;
+  switch (d.out_dtype) {
+    case DT_F32: launch_stem_t<FmtF32>(a, in_layout, smem, st); break;
+    case DT_BF16: launch_stem_t<FmtBF16>(a, in_layout, smem, st); break;
+    case DT_BF16X3: launch_stem_t<FmtBF16X3>(a, in_layout, smem, st); break;
+    default: launch_stem_t<FmtF16X2>(a, in_layout, smem, st); break;
+  }
+  ++g_launches;
+  YB_CUDA(cudaGetLastError());
+  return YOLO_OK;
+}
+
 // ---- pooling (NHWC, channel-contiguous threads) -------------------------------------------------------
-template <typename T, int NP, bool IS_MAX>
-__global__ void pool_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C, int in_cpitch,
+template <class F, bool IS_MAX>
+__global__ void pool_kernel(const typename F::T* __restrict__ in, typename F::T* __restrict__ out, int N, int H, int W, int C, int in_cpitch,
                             int in_coff, long long in_ps, int out_cpitch, int out_coff, long long out_ps, int Ho, int Wo, int k,
                             int stride, int pad) {
   size_t total = (size_t)N * Ho * Wo * C;
@@ -353,12 +504,12 @@ __global__ void pool_kernel(const T* __restrict__ in, T* __restrict__ out, int N
       for (int s = 0; s < k; ++s) {
         int iw = ow * stride - pad + s;
         if ((unsigned)iw >= (unsigned)W) continue;
-        float v = ld1p<NP>(in + ((size_t)(n * H + ih) * W + iw) * in_cpitch + in_coff + c, in_ps);
+        float v = ld1f<F>(in + ((size_t)(n * H + ih) * W + iw) * in_cpitch + in_coff + c, in_ps);
         acc = IS_MAX ? fmaxf(acc, v) : acc + v;
       }
     }
     if (!IS_MAX) acc = acc / (float)(k * k);     // gluon AvgPool2D: count_include_pad, no padding used here
-    store1p<NP>(out + pix * out_cpitch + out_coff + c, out_ps, acc);
+    store1f<F>(out + pix * out_cpitch + out_coff + c, out_ps, acc);
   }
 }
 
@@ -370,12 +521,13 @@ int launch_pool(const void* in, void* out, int dtype, int N, int H, int W, int C
   if (total == 0) return fail(YOLO_E_SHAPE, "pool: empty problem");
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-#define YB_POOL(T, NP, MX)                                                                                              \
-  pool_kernel<T, NP, MX><<<blocks, 256, 0, st>>>(static_cast<const T*>(in), static_cast<T*>(out), N, H, W, C, in_cpitch, \
-                                                 in_coff, in_plane_stride, out_cpitch, out_coff, out_plane_stride, Ho, Wo, k, stride, pad)
-  if (dtype == DT_F32) { if (is_max) YB_POOL(float, 1, true); else YB_POOL(float, 1, false); }
-  else if (dtype == DT_BF16) { if (is_max) YB_POOL(__nv_bfloat16, 1, true); else YB_POOL(__nv_bfloat16, 1, false); }
-  else { if (is_max) YB_POOL(__nv_bfloat16, 3, true); else YB_POOL(__nv_bfloat16, 3, false); }
+#define YB_POOL(F, MX)                                                                                                   \
+  pool_kernel<F, MX><<<blocks, 256, 0, st>>>(static_cast<const F::T*>(in), static_cast<F::T*>(out), N, H, W, C, in_cpitch, \
+                                             in_coff, in_plane_stride, out_cpitch, out_coff, out_plane_stride, Ho, Wo, k, stride, pad)
+  if (dtype == DT_F32) { if (is_max) YB_POOL(FmtF32, true); else YB_POOL(FmtF32, false); }
+  else if (dtype == DT_BF16) { if (is_max) YB_POOL(FmtBF16, true); else YB_POOL(FmtBF16, false); }
+  else if (dtype == DT_BF16X3) { if (is_max) YB_POOL(FmtBF16X3, true); else YB_POOL(FmtBF16X3, false); }
+  else { if (is_max) YB_POOL(FmtF16X2, true); else YB_POOL(FmtF16X2, false); }
 #undef YB_POOL
   ++g_launches;
   YB_CUDA(cudaGetLastError());

@@ -10,9 +10,13 @@
 // GEMM view: D[M x N] = A[M x K] * B[N x K]^T, M = batch*Ho*Wo output pixels, N = Cout, K = kh*kw*Cin,
 // k = (r*kw + s)*Cin + c.  CTA tile 128 x BN, K step 64 (one 128-byte swizzle row of bf16).
 //
-// Precision modes (template NP = operand planes):
-//   NP = 1  bf16 operands, fp32 accumulate.
-//   NP = 3  "bf16x6": every fp32 operand value v is carried as three bf16 planes v = v0 + v1 + v2 (exact
+// Precision modes (template MODE):
+//   MODE 0  bf16: one operand plane, fp32 accumulate.
+//   MODE 2  "fp16x3": every fp32 operand value is carried as two fp16 planes v = v0 + v1 * 2^-11 (22-bit split; v1
+//           stored pre-scaled so it stays a normal fp16 number).  Three plane pairs are multiplied: (0,0) into the
+//           rotating main accumulators, (0,1) and (1,0) into the correction accumulator which the epilogue scales by
+//           2^-11.  The dropped (1,1) pair is 2^-22 relative - the accuracy class of "3xTF32" at twice its rate.
+//   MODE 1  "bf16x6": every fp32 operand value v is carried as three bf16 planes v = v0 + v1 + v2 (exact
 //           24-bit split, written by the producing layer's epilogue / packed once for the weights) and the
 //           product is formed from the six plane pairs with i + j <= 2.  Dropped pairs are <= 2^-24 relative:
 //           fp32-grade operands at 1/6 of the bf16 rate.  The tensor core's fp32 accumulator TRUNCATES (measured:
@@ -27,6 +31,7 @@
 // the 512 TMEM columns (the main loop is 6x longer, the exposed epilogue is a few percent).
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <vector>
@@ -36,25 +41,24 @@
 namespace yb {
 
 constexpr int TILE_M = 128;
-constexpr int BLOCK_K = 64;                 // bf16 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int A_TILE_BYTES = TILE_M * BLOCK_K * 2;      // 16 KB per plane
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 320;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct UmmaParams {
   int M, Cout, BN, n_tiles_n, n_tiles;
   int taps, kw, cin_blocks;                 // k-blocks = taps * cin_blocks
+  int bk;                                   // K elements per pipeline stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows)
   int Ho, Wo, stride, pad;
   int in_coff;
   int a_plane_n;                            // images per plane in the folded N dimension (= max_batch)
   int b_plane_rows;                         // weight rows per plane (= padded Cout)
   int stages;
+  int flush;                                // k-blocks per TMEM partial sum (two-level accumulation)
   // epilogue
   const float* scale;  const float* shift;  int act;
-  const void* res;  int res_cpitch, res_coff;  long long res_plane_stride;   // elements
+  const void* res;  int res_dtype, res_cpitch, res_coff;  long long res_plane_stride;   // elements
   void* out;  int out_dtype;  int out_cpitch, out_coff;  long long out_plane_stride;  int upsample2;
 };
 
@@ -100,19 +104,21 @@ __device__ __forceinline__ void prefetch_tmap(const void* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (tile rows are 128 bytes; 8-row groups 1024 bytes apart).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+// K-major shared-memory matrix descriptor.  Tile rows are `row_bytes` (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B) and
+// 8-row groups are 8*row_bytes apart (stride byte offset).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);             // start address            bits [0,14)
   d |= (uint64_t)1 << 16;                               // leading byte offset      bits [16,30) (ignored for swizzled K-major; CuTe writes 1)
-  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset       bits [32,46)
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;          // stride byte offset       bits [32,46)
   d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                               // layout: SWIZZLE_128B
+  d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;      // layout: SWIZZLE_128B = 2, SWIZZLE_64B = 4
   return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128.
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+// kind::f16 instruction descriptor: (bf16 | fp16) x same -> fp32, both operands K-major, M = 128.
+__device__ __forceinline__ uint32_t make_idesc(int n, bool fp16) {
+  const uint32_t fmt = fp16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -147,32 +153,48 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 // ---------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------
-template <int NP>
+// Two-level accumulation.  The tensor core's fp32 accumulator truncates (round toward zero: a bias of ~1e-8 of
+// |acc| per MMA, measured in profiles/r1_umma_precision.txt), which after thousands of MMAs per output is 10-40x the
+// rounding noise of an fp32 FMA chain.  So a TMEM accumulator only ever holds a short PARTIAL sum (p.flush k-blocks =
+// 8 MMAs of the leading product); the accumulation warps add each partial into fp32 REGISTERS with round-to-nearest
+// while the MMA warp already fills the other TMEM partial buffer.  The small correction products of the split
+// precisions (2^-11 / 2^-8 of the result) may accumulate in TMEM over the whole K: their truncation is negligible.
+//
+// Warps: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = accumulation/epilogue group 0, 6..9 = group 1.
+// Groups alternate tiles: while one group converts/stores tile i from its registers, the other one is already
+// accumulating the partials of tile i+1 - the epilogue is fully overlapped with the main loop.
+constexpr int GROUP_THREADS = 128;
+
+template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ UmmaParams p) {
+  constexpr int NP = MODE == 0 ? 1 : (MODE == 1 ? 3 : 2);          // operand planes
+  constexpr int N_PAIRS = MODE == 0 ? 1 : (MODE == 1 ? 6 : 3);     // plane pairs multiplied per k-step
+  constexpr bool HAS_CORR = MODE != 0;
+  const int A_TILE_BYTES = TILE_M * p.bk * 2;
+  const int row_bytes = p.bk * 2;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve: [stages][NP A tiles | NP B tiles] then barriers, tmem pointer, scale/shift staging
+  // carve: [stages][NP A tiles | NP B tiles] then barriers, tmem pointer, scale/shift staging (one copy per group)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int b_tile_bytes = p.BN * BLOCK_K * 2;
+  const int b_tile_bytes = p.BN * p.bk * 2;
   const int stage_bytes = NP * (A_TILE_BYTES + b_tile_bytes);
   const uint32_t tiles_end = smem_base + p.stages * stage_bytes;
   unsigned char* aux = smem_gen + (size_t)p.stages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux);                 // full[8] empty[8] tfull[2] tempty[2]
+  // barrier layout (8 bytes each): full[8] empty[8] pfull[2] pempty[2] cfull[2] cempty[2]
   const uint32_t bar_full = tiles_end, bar_empty = tiles_end + 8 * MAX_STAGES;
-  const uint32_t bar_tfull = tiles_end + 16 * MAX_STAGES, bar_tempty = bar_tfull + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 16 * MAX_STAGES + 32);
-  float* s_scale = reinterpret_cast<float*>(aux + 16 * MAX_STAGES + 64);      // [2][BN]: scale, shift
-  (void)bars;
+  const uint32_t bar_pfull = tiles_end + 16 * MAX_STAGES, bar_pempty = bar_pfull + 16;
+  const uint32_t bar_cfull = bar_pfull + 32, bar_cempty = bar_pfull + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 16 * MAX_STAGES + 64);
+  float* s_scale_all = reinterpret_cast<float*>(aux + 16 * MAX_STAGES + 128);      // [group][2][BN]: scale, shift
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // TMEM: NP == 1: two buffers of one accumulator; NP == 3: one buffer of four accumulators (3 main + 1 correction)
-  constexpr int N_ACC = NP == 1 ? 1 : 4;
-  constexpr int N_BUF = NP == 1 ? 2 : 1;
-  const int acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
-  const int tmem_cols = NP == 1 ? 2 * acc_stride : 512;
+  // TMEM: two partial buffers for the leading product + two correction buffers (tile parity), each `acc_stride` columns
+  const int acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : 128);
+  const int tmem_cols = HAS_CORR ? 4 * acc_stride : (2 * acc_stride < 32 ? 32 : 2 * acc_stride);
   const int nkb = p.taps * p.cin_blocks;
+  const int npart = (nkb + p.flush - 1) / p.flush;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_a);
@@ -182,10 +204,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, EPI_THREADS / 32);
+      mbar_init(bar_pfull + 8 * b, 1);
+      mbar_init(bar_pempty + 8 * b, GROUP_THREADS / 32);
+      mbar_init(bar_cfull + 8 * b, 1);
+      mbar_init(bar_cempty + 8 * b, GROUP_THREADS / 32);
     }
-    static_assert(N_ACC * N_BUF <= 4, "TMEM budget");
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -219,9 +242,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t sb = sa + NP * A_TILE_BYTES;
 #pragma unroll
           for (int pl = 0; pl < NP; ++pl) {
-            tma_load_im2col_4d(sa + pl * A_TILE_BYTES, &map_a, full, p.in_coff + cb * BLOCK_K, bw, bh, img + pl * p.a_plane_n,
+            tma_load_im2col_4d(sa + pl * A_TILE_BYTES, &map_a, full, p.in_coff + cb * p.bk, bw, bh, img + pl * p.a_plane_n,
                                (uint16_t)s, (uint16_t)r);
-            tma_load_2d(sb + pl * b_tile_bytes, &map_b, full, kb * BLOCK_K, n0 + pl * p.b_plane_rows);
+            tma_load_2d(sb + pl * b_tile_bytes, &map_b, full, kb * p.bk, n0 + pl * p.b_plane_rows);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -230,73 +253,146 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.BN);
+      const uint32_t idesc = make_idesc(p.BN, MODE == 2);
+      const int ksteps = p.bk / UMMA_K;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      uint32_t pcount = 0;                                                     // partial buffers handed out so far
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int buf = N_BUF == 2 ? (it & 1) : 0;
-        const uint32_t use = N_BUF == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
-        mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);                       // epilogue has drained this accumulator set
-        tc_fence_after();
-        const uint32_t tmem_buf = tmem_base + buf * N_ACC * acc_stride;
-        uint32_t written = 0;                                                  // accumulators already holding a partial sum
+        const int cbuf = it & 1;
+        if (HAS_CORR) {
+          mbar_wait(bar_cempty + 8 * cbuf, (((uint32_t)it >> 1) & 1) ^ 1);     // correction buffer drained (tile it-2)
+          tc_fence_after();
+        }
+        const uint32_t tmem_corr = tmem_base + (2 + cbuf) * acc_stride;
+        uint32_t corr_written = 0;
+        uint32_t tmem_main = 0;
+        uint32_t main_written = 0;
+        int pbuf = 0;
         for (int kb = 0; kb < nkb; ++kb) {
+          if (kb % p.flush == 0) {                                             // start a new partial sum
+            pbuf = pcount & 1;
+            mbar_wait(bar_pempty + 8 * pbuf, ((pcount >> 1) & 1) ^ 1);
+            tc_fence_after();
+            tmem_main = tmem_base + pbuf * acc_stride;
+            main_written = 0;
+          }
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = sa + NP * A_TILE_BYTES;
-          const int main_acc = NP == 1 ? 0 : kb % 3;
 #pragma unroll
-          for (int pair = 0; pair < (NP == 1 ? 1 : 6); ++pair) {
-            int pa, pb, acc;
-            if (NP == 1) { pa = 0; pb = 0; acc = 0; }
-            else {
-              constexpr int PA[6] = {0, 0, 1, 0, 1, 2};
-              constexpr int PB[6] = {0, 1, 0, 2, 1, 0};
-              pa = PA[pair]; pb = PB[pair];
-              acc = pair == 0 ? main_acc : 3;
-            }
-            const uint32_t tmem_d = tmem_buf + acc * acc_stride;
-            const uint64_t adesc = make_smem_desc(sa + pa * A_TILE_BYTES);
-            const uint64_t bdesc = make_smem_desc(sb + pb * b_tile_bytes);
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              umma_bf16(tmem_d, adesc + (uint64_t)((k * UMMA_K * 2) >> 4), bdesc + (uint64_t)((k * UMMA_K * 2) >> 4), idesc,
-                        (written >> acc) & 1u);
-              written |= 1u << acc;
+          for (int pair = 0; pair < N_PAIRS; ++pair) {
+            // pair 0 = leading product (plane 0 x plane 0) -> partial buffer; the rest -> correction accumulator
+            constexpr int PA6[6] = {0, 0, 1, 0, 1, 2}, PB6[6] = {0, 1, 0, 2, 1, 0};
+            constexpr int PA3[3] = {0, 0, 1}, PB3[3] = {0, 1, 0};
+            const int pa = MODE == 0 ? 0 : (MODE == 1 ? PA6[pair] : PA3[pair]);
+            const int pb = MODE == 0 ? 0 : (MODE == 1 ? PB6[pair] : PB3[pair]);
+            const uint64_t adesc = make_smem_desc(sa + pa * A_TILE_BYTES, row_bytes);
+            const uint64_t bdesc = make_smem_desc(sb + pb * b_tile_bytes, row_bytes);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+              if (pair == 0) {
+                umma_bf16(tmem_main, adesc + koff, bdesc + koff, idesc, main_written);
+                main_written = 1;
+              } else {
+                umma_bf16(tmem_corr, adesc + koff, bdesc + koff, idesc, corr_written);
+                corr_written = 1;
+              }
             }
           }
           umma_commit(bar_empty + 8 * stage);                                 // frees the smem stage when the MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if ((kb + 1) % p.flush == 0 || kb + 1 == nkb) {                      // partial complete -> accumulation warps
+            umma_commit(bar_pfull + 8 * pbuf);
+            ++pcount;
+          }
         }
-        umma_commit(bar_tfull + 8 * buf);                                     // accumulators complete -> epilogue
+        if (HAS_CORR) umma_commit(bar_cfull + 8 * cbuf);
       }
     }
   } else {
-    // =========================== epilogue (warps 2..5) ===========================
-    const int et = threadIdx.x - 64;                       // 0..127
+    // =========================== accumulation + epilogue groups (warps 2..5 and 6..9) ===========================
+    const int group = (warp - 2) >> 2;                     // 0 or 1
+    const int et = threadIdx.x - 64 - group * GROUP_THREADS;   // 0..127 within the group
     const int lane_grp = warp & 3;                         // TMEM lane quarter this warp may access
     const int row = lane_grp * 32 + lane;                  // accumulator row = pixel within the tile
     const int HoWo = p.Ho * p.Wo;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    float* s_scale = s_scale_all + group * 2 * p.BN;
+    const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
+    const int nchunks = (p.BN + 31) >> 5;
+    int it = group;
+    // Accumulation turns.  An mbarrier parity wait can only tell "this phase" from "the previous one", so a group must
+    // not start waiting for its partials before the other group has consumed all of the preceding tile's partials:
+    // named barriers 3/4 pass the turn (FA3-style ping-pong); group 1 donates the first turn to group 0.
+    if (group == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");
+    for (int tile = blockIdx.x + group * gridDim.x; tile < p.n_tiles; tile += 2 * gridDim.x, it += 2) {
       const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
       const int m0 = mt * TILE_M, n0 = nt * p.BN;
-      const int buf = N_BUF == 2 ? (it & 1) : 0;
-      const uint32_t use = N_BUF == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
-      // stage scale/shift of this tile's columns (previous tile's readers are past their last use: see barrier below)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = et; i < p.BN; i += EPI_THREADS) {
+      // stage scale/shift of this tile's columns (the group's previous tile is completely finished here)
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+      for (int i = et; i < p.BN; i += GROUP_THREADS) {
         const int n = n0 + i;
         s_scale[i] = (p.scale && n < p.Cout) ? __ldg(p.scale + n) : 1.f;
         s_scale[p.BN + i] = (p.shift && n < p.Cout) ? __ldg(p.shift + n) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(bar_tfull + 8 * buf, use & 1);
-      tc_fence_after();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+
+      float acc[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[c][i] = 0.f;
+
+      // ---- level 2: add the TMEM partial sums into registers (round-to-nearest) ----
+      asm volatile("bar.sync %0, 256;" ::"r"(3 + group) : "memory");                      // my turn
+      uint32_t pc = (uint32_t)it * (uint32_t)npart;
+      for (int part = 0; part < npart; ++part, ++pc) {
+        const int pbuf = pc & 1;
+        mbar_wait(bar_pfull + 8 * pbuf, (pc >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_addr + pbuf * acc_stride;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nchunks) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[c][i] += __uint_as_float(v[i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pempty + 8 * pbuf);
+      }
+      if (HAS_CORR) {
+        const int cbuf = it & 1;
+        mbar_wait(bar_cfull + 8 * cbuf, ((uint32_t)it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_addr + (2 + cbuf) * acc_stride;
+        const float cw = MODE == 2 ? kF16LoScaleInv : 1.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nchunks) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[c][i] = fmaf(__uint_as_float(v[i]), cw, acc[c][i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_cempty + 8 * cbuf);
+      }
+
+      asm volatile("bar.arrive %0, 256;" ::"r"(4 - group) : "memory");                    // the other group's turn
+
+      // ---- epilogue from registers: BN affine, activation, residual, format split, store ----
       const int m = m0 + row;
-      const bool m_ok = m < p.M;
+      if (m >= p.M) continue;
       size_t pix[4];
       int npix = 1;
       if (p.upsample2) {
@@ -308,55 +404,39 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       } else {
         pix[0] = (size_t)m;
       }
-      const uint32_t taddr_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + buf * N_ACC * acc_stride;
-      const int n_main = NP == 1 ? 1 : (nkb < 3 ? nkb : 3);                   // main accumulators that were written
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr_row + c0, v);
-        tmem_ld_wait();
-        if (NP == 3) {                                                         // ((D0a + D0b) + D0c) + Dcorr, fp32 RN
-          uint32_t u[32];
-          for (int a = 1; a < n_main; ++a) {
-            tmem_ld_32x32b_x32(taddr_row + a * acc_stride + c0, u);
-            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
-          }
-          tmem_ld_32x32b_x32(taddr_row + 3 * acc_stride + c0, u);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
-        }
-        if (c0 + 32 >= p.BN) {                              // last chunk read: hand the accumulator back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-        }
+      for (int c = 0; c < 4; ++c) {
+        const int c0 = c * 32;
         const int nb = n0 + c0;
-        if (!m_ok || nb >= p.Cout) continue;
-        float y[32];
+        if (c >= nchunks || nb >= p.Cout) continue;
+        float* y = acc[c];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float t = fmaf(__uint_as_float(v[i]), s_scale[c0 + i], s_scale[p.BN + c0 + i]);
+          float t = fmaf(y[i], s_scale[c0 + i], s_scale[p.BN + c0 + i]);
           if (p.act == ACT_LEAKY) t = t > 0.f ? t : 0.1f * t;
           else if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
           y[i] = t;
         }
         const int nvalid = min(32, p.Cout - nb);
-        if (p.res) {                                        // residual add (DarknetBasicBlockV3), same format as the output
-          const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(p.res) + (size_t)m * p.res_cpitch + p.res_coff + nb;
-#pragma unroll
-          for (int pl = 0; pl < NP; ++pl) {
+        if (p.res) {                                        // residual add (DarknetBasicBlockV3), stored in the activation format
+          const int rnp = p.res_dtype == DT_BF16X3 ? 3 : (p.res_dtype == DT_F16X2 ? 2 : 1);
+          const unsigned short* rp = static_cast<const unsigned short*>(p.res) + (size_t)m * p.res_cpitch + p.res_coff + nb;
+          for (int pl = 0; pl < rnp; ++pl) {
             const uint4* r4 = reinterpret_cast<const uint4*>(rp + (size_t)pl * p.res_plane_stride);
+            const float pw = (p.res_dtype == DT_F16X2 && pl == 1) ? kF16LoScaleInv : 1.f;
+            uint4 u4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) u4[q] = __ldg(r4 + q);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint4 u = __ldg(r4 + q);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+              const uint32_t uu[4] = {u4[q].x, u4[q].y, u4[q].z, u4[q].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float2 f = __bfloat1622float2(h2[e]);
-                y[q * 8 + 2 * e] += f.x;
-                y[q * 8 + 2 * e + 1] += f.y;
+                float2 f;
+                if (p.res_dtype == DT_F16X2) f = __half22float2(*reinterpret_cast<const __half2*>(&uu[e]));
+                else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uu[e]));
+                y[q * 8 + 2 * e] = fmaf(f.x, pw, y[q * 8 + 2 * e]);
+                y[q * 8 + 2 * e + 1] = fmaf(f.y, pw, y[q * 8 + 2 * e + 1]);
               }
             }
           }
@@ -366,36 +446,47 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (nvalid == 32 && ((p.out_cpitch | p.out_coff) & 3) == 0) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(op)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-          } else if (((p.out_cpitch | p.out_coff) & 1) == 0 && (nvalid & 1) == 0) {
-            for (int i = 0; i < nvalid; i += 2) *reinterpret_cast<float2*>(op + i) = make_float2(y[i], y[i + 1]);
+          } else if (((p.out_cpitch | p.out_coff) & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2)
+              if (i + 1 < nvalid) *reinterpret_cast<float2*>(op + i) = make_float2(y[i], y[i + 1]);
+              else if (i < nvalid) op[i] = y[i];
           } else {
-            for (int i = 0; i < nvalid; ++i) op[i] = y[i];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) op[i] = y[i];
           }
         } else {
-          // bf16 planes: v = v0 + v1 + v2 (exact split); NP == 1 keeps only v0
-          uint32_t w[NP][16];
+          // split into the planes of the activation format and store 64 contiguous bytes per plane
+          const int onp = p.out_dtype == DT_BF16X3 ? 3 : (p.out_dtype == DT_F16X2 ? 2 : 1);
+          for (int pl = 0; pl < onp; ++pl) {
+            uint32_t w[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float a = y[i], b = y[i + 1];
-#pragma unroll
-            for (int pl = 0; pl < NP; ++pl) {
-              float ha = bf16_round(a), hb = bf16_round(b);
-              w[pl][i >> 1] = pack_bf16(ha, hb);
-              a -= ha; b -= hb;
+            for (int i = 0; i < 32; i += 2) {
+              float a = y[i], b = y[i + 1];
+              if (p.out_dtype == DT_F16X2) {
+                a = fminf(fmaxf(a, -kF16Max), kF16Max); b = fminf(fmaxf(b, -kF16Max), kF16Max);
+                __half2 h = __floats2half2_rn(a, b);
+                w[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                if (pl == 0) {
+                  float2 f = __half22float2(h);
+                  y[i] = (y[i] - f.x) * kF16LoScale; y[i + 1] = (y[i + 1] - f.y) * kF16LoScale;     // exact: remainder has <= 13 bits
+                }
+              } else {
+                float ha = bf16_round(a), hb = bf16_round(b);
+                w[i >> 1] = pack_bf16(ha, hb);
+                y[i] = a - ha; y[i + 1] = b - hb;
+              }
             }
-          }
-          for (int q = 0; q < npix; ++q) {
-#pragma unroll
-            for (int pl = 0; pl < NP; ++pl) {
-              __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out) + (size_t)pl * p.out_plane_stride + pix[q] * p.out_cpitch + p.out_coff + nb;
+            for (int q = 0; q < npix; ++q) {
+              unsigned short* op = static_cast<unsigned short*>(p.out) + (size_t)pl * p.out_plane_stride + pix[q] * p.out_cpitch + p.out_coff + nb;
               if (nvalid == 32) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) reinterpret_cast<uint4*>(op)[g] = make_uint4(w[pl][4 * g], w[pl][4 * g + 1], w[pl][4 * g + 2], w[pl][4 * g + 3]);
+                for (int g = 0; g < 4; ++g) reinterpret_cast<uint4*>(op)[g] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
               } else {
-                for (int i = 0; i < nvalid; ++i) {
-                  uint32_t u = w[pl][i >> 1];
-                  reinterpret_cast<unsigned short*>(op)[i] = (i & 1) ? (unsigned short)(u >> 16) : (unsigned short)(u & 0xFFFFu);
-                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < nvalid) op[i] = (i & 1) ? (unsigned short)(w[i >> 1] >> 16) : (unsigned short)(w[i >> 1] & 0xFFFFu);
               }
             }
           }
@@ -446,10 +537,17 @@ static inline float bf2f(unsigned short h) {
   memcpy(&f, &u, 4);
   return f;
 }
+static inline unsigned short f2h(float f) { __half h = __float2half_rn(f); unsigned short u; memcpy(&u, &h, 2); return u; }
+static inline float h2f(unsigned short u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
 
 static int pick_bn(int cout) {
   int c16 = (cout + 15) & ~15;
   return c16 < 128 ? c16 : 128;
+}
+static int mode_of(int precision) { return precision == YOLO_PREC_BF16 ? 0 : (precision == YOLO_PREC_BF16X6 ? 1 : 2); }
+static int planes_of(int precision) { return precision == YOLO_PREC_BF16 ? 1 : (precision == YOLO_PREC_BF16X6 ? 3 : 2); }
+static int act_dtype_of(int precision) {
+  return precision == YOLO_PREC_BF16 ? DT_BF16 : (precision == YOLO_PREC_BF16X6 ? DT_BF16X3 : DT_F16X2);
 }
 
 int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int cout, int cin, int kh, int kw, int stride,
@@ -460,10 +558,11 @@ int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int co
   const char* dis = getenv("YOLO_B200_DISABLE_UMMA");
   if (dis && dis[0] == '1') return YOLO_OK;
   // shapes the tensor-core kernel takes; everything else stays on the FFMA kernel
-  if (cin % BLOCK_K != 0 || has_prologue || out_nchw || kh != kw || (in_dtype != DT_BF16 && in_dtype != DT_BF16X3)) return YOLO_OK;
+  if (cin % 32 != 0 || has_prologue || out_nchw || kh != kw || in_dtype != act_dtype_of(precision)) return YOLO_OK;
   if (stride < 1 || stride > 8 || pad > 127) return YOLO_OK;
-  const int np = precision == YOLO_PREC_BF16X6 ? 3 : 1;
+  const int np = planes_of(precision);
   u.precision = precision; u.cout = cout; u.cin = cin; u.kh = kh; u.kw = kw; u.stride = stride; u.pad = pad;
+  u.bk = cin % 64 == 0 ? 64 : 32;
   u.bn_tile = pick_bn(cout);
   const int n_tiles_n = (cout + u.bn_tile - 1) / u.bn_tile;
   const int rows = n_tiles_n * u.bn_tile;                  // zero padded so a weight tile never crosses a plane
@@ -475,10 +574,16 @@ int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int co
         for (int s = 0; s < kw; ++s) {
           float v = w_oihw[(((size_t)o * cin + c) * kh + r) * kw + s];
           const size_t k = (size_t)(r * kw + s) * cin + c;
-          for (int pl = 0; pl < np; ++pl) {
-            unsigned short h = f2bf(v);
-            host[((size_t)pl * rows + o) * K + k] = h;
-            v -= bf2f(h);
+          if (precision == YOLO_PREC_FP16X3) {
+            unsigned short h0 = f2h(v);
+            host[((size_t)0 * rows + o) * K + k] = h0;
+            host[((size_t)1 * rows + o) * K + k] = f2h((v - h2f(h0)) * kF16LoScale);
+          } else {
+            for (int pl = 0; pl < np; ++pl) {
+              unsigned short h = f2bf(v);
+              host[((size_t)pl * rows + o) * K + k] = h;
+              v -= bf2f(h);
+            }
           }
         }
   if (u.w_packed) { cudaFree(u.w_packed); u.w_packed = nullptr; }
@@ -488,13 +593,14 @@ int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int co
   YB_CUDA(cudaStreamSynchronize(st));
   int rc = load_driver_entry_points();
   if (rc) return rc;
+  const CUtensorMapDataType dt = precision == YOLO_PREC_FP16X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = u.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)np * rows};
   cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)u.bn_tile};
+  cuuint32_t box[2] = {(cuuint32_t)u.bk, (cuuint32_t)u.bn_tile};
   cuuint32_t estr[2] = {1, 1};
-  CUresult cr = g_encode_tiled(reinterpret_cast<CUtensorMap*>(u.map_b), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, u.w_packed, gdim, gstr, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult cr = g_encode_tiled(reinterpret_cast<CUtensorMap*>(u.map_b), dt, 2, u.w_packed, gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(YOLO_E_CUDA, "cuTensorMapEncodeTiled(weights %dx%zu) failed: %d", np * rows, K, (int)cr);
   u.eligible = true;
   return YOLO_OK;
@@ -505,17 +611,18 @@ int umma_build_maps(UmmaConv& u, void* in_base, int max_batch, int H, int W, int
   if (!u.eligible) return YOLO_OK;
   int rc = load_driver_entry_points();
   if (rc) return rc;
-  const int np = u.precision == YOLO_PREC_BF16X6 ? 3 : 1;
+  const int np = planes_of(u.precision);
   if (cpitch % 8 != 0 || (reinterpret_cast<uintptr_t>(in_base) & 15)) return YOLO_OK;       // TMA stride/address alignment
   (void)C; (void)coff;
+  const CUtensorMapDataType dt = u.precision == YOLO_PREC_FP16X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = u.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   cuuint64_t gdim[4] = {(cuuint64_t)cpitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)np * max_batch};
   cuuint64_t gstr[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2};
   int lower[2] = {-u.pad, -u.pad};
   int upper[2] = {u.pad - (u.kw - 1), u.pad - (u.kh - 1)};
   cuuint32_t estr[4] = {1, (cuuint32_t)u.stride, (cuuint32_t)u.stride, 1};
-  CUresult cr = g_encode_im2col(reinterpret_cast<CUtensorMap*>(u.map_a), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in_base, gdim, gstr, lower, upper,
-                                BLOCK_K, TILE_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult cr = g_encode_im2col(reinterpret_cast<CUtensorMap*>(u.map_a), dt, 4, in_base, gdim, gstr, lower, upper, (cuuint32_t)u.bk, TILE_M, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS)
     return fail(YOLO_E_CUDA, "cuTensorMapEncodeIm2col(C=%d W=%d H=%d N=%d k=%d s=%d p=%d) failed: %d", cpitch, W, H, np * max_batch, u.kw, u.stride, u.pad, (int)cr);
   u.max_batch = max_batch;
@@ -531,16 +638,16 @@ void umma_release(UmmaConv& u) {
 
 static int g_num_sms = 0;
 
-template <int NP>
-static int launch_np(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
+template <int MODE>
+static int launch_mode(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    YB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    YB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
-  conv_umma_kernel<NP><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
-                                                              *reinterpret_cast<const CUtensorMap*>(u.map_b), p);
+  conv_umma_kernel<MODE><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
+                                                                *reinterpret_cast<const CUtensorMap*>(u.map_b), p);
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
@@ -554,35 +661,41 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
     YB_CUDA(cudaGetDevice(&dev));
     YB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int np = u.precision == YOLO_PREC_BF16X6 ? 3 : 1;
+  const int np = planes_of(u.precision);
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.M = d.N * d.Ho * d.Wo;
   p.Cout = d.Cout;
   p.BN = u.bn_tile;
+  p.bk = u.bk;
   p.n_tiles_n = (d.Cout + p.BN - 1) / p.BN;
   p.n_tiles = ((p.M + TILE_M - 1) / TILE_M) * p.n_tiles_n;
-  p.taps = d.kh * d.kw; p.kw = d.kw; p.cin_blocks = d.Cin / BLOCK_K;
+  p.taps = d.kh * d.kw; p.kw = d.kw; p.cin_blocks = d.Cin / p.bk;
   p.Ho = d.Ho; p.Wo = d.Wo; p.stride = d.stride; p.pad = d.pad;
   p.in_coff = d.in_coff;
   p.a_plane_n = u.max_batch;
   p.b_plane_rows = p.n_tiles_n * p.BN;
-  const int stage_bytes = np * (A_TILE_BYTES + p.BN * BLOCK_K * 2);
-  const int aux_bytes = 16 * MAX_STAGES + 64 + 2 * p.BN * 4 + 64;
+  const int stage_bytes = np * (TILE_M * p.bk * 2 + p.BN * p.bk * 2);
+  const int aux_bytes = 16 * MAX_STAGES + 128 + 2 * 2 * p.BN * 4 + 64;
+  p.flush = p.bk == 64 ? 2 : 4;             // 8 MMAs of the leading product per partial
   int stages = (SMEM_LIMIT - 1024 - aux_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return fail(YOLO_E_UNSUPPORTED, "umma: tile does not fit two pipeline stages");
   p.stages = stages;
   p.scale = d.scale; p.shift = d.shift; p.act = d.act;
-  p.res = d.res; p.res_cpitch = d.res_cpitch; p.res_coff = d.res_coff;
+  p.res = d.res; p.res_dtype = d.out_dtype; p.res_cpitch = d.res_cpitch; p.res_coff = d.res_coff;
   p.out = d.out; p.out_dtype = d.out_dtype; p.out_cpitch = d.out_cpitch; p.out_coff = d.out_coff; p.upsample2 = d.upsample2;
   p.res_plane_stride = d.res_plane_stride;
   p.out_plane_stride = d.out_plane_stride;
-  if (d.out_dtype != DT_F32 && ((d.out_cpitch | d.out_coff) & 7)) return fail(YOLO_E_UNSUPPORTED, "umma: bf16 output needs 16-byte aligned channel slices");
+  if (d.out_dtype != DT_F32 && ((d.out_cpitch | d.out_coff) & 7)) return fail(YOLO_E_UNSUPPORTED, "umma: 16-bit output needs 16-byte aligned channel slices");
   if (d.res && ((d.res_cpitch | d.res_coff) & 7)) return fail(YOLO_E_UNSUPPORTED, "umma: residual needs 16-byte aligned channel slices");
-  if (d.res && d.Cout % 32) return fail(YOLO_E_UNSUPPORTED, "umma: residual needs Cout %% 32 == 0");
+  if (d.res && (d.Cout % 32 || d.out_dtype == DT_F32)) return fail(YOLO_E_UNSUPPORTED, "umma: residual needs Cout %% 32 == 0 and a 16-bit activation format");
   const int smem_bytes = 1024 + stages * stage_bytes + aux_bytes;
-  return np == 3 ? launch_np<3>(u, p, smem_bytes, st) : launch_np<1>(u, p, smem_bytes, st);
+  switch (mode_of(u.precision)) {
+    case 0: return launch_mode<0>(u, p, smem_bytes, st);
+    case 1: return launch_mode<1>(u, p, smem_bytes, st);
+    default: return launch_mode<2>(u, p, smem_bytes, st);
+  }
 }
 
 }  // namespace yb

@@ -10,8 +10,8 @@ struct UmmaConv {
   int precision = 0;
   int cout = 0, cin = 0, kh = 1, kw = 1, stride = 1, pad = 0;
   int bn_tile = 0;            // N tile (UMMA N)
-  int bk = 64;                // K elements per pipeline stage (one 128-byte swizzle row)
-  void* w_packed = nullptr;   // device: [cout_padded][K] bf16, K-major, k = (r*kw+s)*Cin + c
+  int bk = 64;                // K elements per pipeline stage: 64 (128-byte swizzle rows) or 32 (64-byte rows, Cin % 64 != 0)
+  void* w_packed = nullptr;   // device: [planes][cout_padded][K] 16-bit, K-major, k = (r*kw+s)*Cin + c
   size_t w_bytes = 0;
   alignas(64) unsigned char map_a[128];   // CUtensorMap (im2col) for the activations
   alignas(64) unsigned char map_b[128];   // CUtensorMap (tiled)  for the weights

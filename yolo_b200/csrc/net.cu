@@ -11,6 +11,7 @@
 // epilogues, DenseNet pre-activation BN->ReLU in conv prologues, upsample+concat and DenseNet concat are
 // channel-offset writes into a shared buffer, and the YOLOOutput transpose disappears because the NHWC
 // result of the 1x1 head conv already is (B, H*W, A, C).
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -146,7 +147,7 @@ struct Builder {
   View new_buffer(int H, int W, int C, int dtype) {
     Buffer b;
     b.dtype = dtype;
-    b.bytes_per_image = (size_t)H * W * C * (dtype == DT_F32 ? 4 : (dtype == DT_BF16 ? 2 : 6));
+    b.bytes_per_image = (size_t)H * W * C * dtype_bytes_per_elem(dtype);
     h->bufs.push_back(b);
     View v;
     v.buf = (int)h->bufs.size() - 1;
@@ -402,11 +403,11 @@ extern "C" int yolo_create(const yolo_spec* spec, int device, yolo_handle** out)
   if (!spec || !out) return fail(YOLO_E_BADARG, "create: null spec/out");
   *out = nullptr;
   if (spec->max_batch < 1) return fail(YOLO_E_BADARG, "create: max_batch=%d", spec->max_batch);
-  if (spec->precision < YOLO_PREC_FP32 || spec->precision > YOLO_PREC_BF16X6) return fail(YOLO_E_BADARG, "create: precision=%d", spec->precision);
+  if (spec->precision < YOLO_PREC_FP32 || spec->precision > YOLO_PREC_FP16X3) return fail(YOLO_E_BADARG, "create: precision=%d", spec->precision);
   std::unique_ptr<yolo_handle> h(new yolo_handle());
   h->spec = *spec;
   h->device = device;
-  h->act_dtype = spec->precision == YOLO_PREC_BF16 ? DT_BF16 : (spec->precision == YOLO_PREC_BF16X6 ? DT_BF16X3 : DT_F32);
+  h->act_dtype = spec->precision == YOLO_PREC_BF16 ? DT_BF16 : (spec->precision == YOLO_PREC_BF16X6 ? DT_BF16X3 : (spec->precision == YOLO_PREC_FP16X3 ? DT_F16X2 : DT_F32));
   Builder b(h.get());
   int rc;
   switch (spec->net_type) {
@@ -568,6 +569,12 @@ extern "C" int yolo_set_workspace(yolo_handle* h, void* device_ptr, size_t bytes
     for (auto& op : h->ops) {
       if (op.kind != OP_CONV || !op.umma.eligible) continue;
       if (op.in.buf < 0) { op.umma.enabled = false; continue; }
+      // epilogue constraints of the tensor-core kernel: 16-byte aligned 16-bit channel slices, 32-column residual chunks
+      const bool out16 = op.out.dtype != DT_F32;
+      if ((out16 && ((op.out.cpitch | op.out.coff) & 7)) || (op.has_res && (((op.res.cpitch | op.res.coff) & 7) || op.cout % 32 || !out16))) {
+        op.umma.enabled = false;
+        continue;
+      }
       int rc = umma_build_maps(op.umma, h->ws + h->bufs[op.in.buf].offset, h->spec.max_batch, op.in.H, op.in.W, op.in.C,
                                op.in.cpitch, op.in.coff);
       if (rc) return hfail(h, rc);
@@ -631,6 +638,7 @@ extern "C" int yolo_forward(yolo_handle* h, const void* input, int batch, int in
       d.upsample2 = op.upsample2; d.out_nchw = op.out_nchw;
       const int lay = op.in.buf == -1 ? (in_layout == YOLO_IN_NCHW_F32 ? 1 : 2) : 0;
       if (op.umma.enabled) rc = launch_conv_umma(op.umma, d, st);
+      else if (stem_eligible(d, lay)) rc = launch_stem(d, lay, st);
       else rc = launch_conv_simt(d, lay, st);
     }
     if (rc) return hfail(h, rc);
@@ -650,7 +658,7 @@ extern "C" int yolo_debug_activation(yolo_handle* h, const char* layer_name, int
   YB_CUDA(cudaSetDevice(h->device));
   YB_CUDA(cudaDeviceSynchronize());
   const size_t esz = v.dtype == DT_F32 ? 4 : 2;
-  const int nplanes = v.dtype == DT_BF16X3 ? 3 : 1;
+  const int nplanes = dtype_planes(v.dtype);
   const size_t nraw = (size_t)(nplanes - 1) * v.ps + (size_t)batch * v.H * v.W * v.cpitch;
   std::vector<unsigned char> raw(nraw * esz);
   YB_CUDA(cudaMemcpy(raw.data(), h->ws + h->bufs[v.buf].offset, raw.size(), cudaMemcpyDeviceToHost));
@@ -663,9 +671,15 @@ extern "C" int yolo_debug_activation(yolo_handle* h, const char* layer_name, int
           if (v.dtype != DT_F32) {
             for (int pl = 0; pl < nplanes; ++pl) {
               unsigned short u = reinterpret_cast<unsigned short*>(raw.data())[src + (size_t)pl * v.ps];
-              unsigned int w = (unsigned int)u << 16;
               float t;
-              memcpy(&t, &w, 4);
+              if (v.dtype == DT_F16X2) {
+                __half hh;
+                memcpy(&hh, &u, 2);
+                t = __half2float(hh) * (pl == 1 ? kF16LoScaleInv : 1.f);
+              } else {
+                unsigned int w = (unsigned int)u << 16;
+                memcpy(&t, &w, 4);
+              }
               f += t;
             }
           } else f = reinterpret_cast<float*>(raw.data())[src];
