@@ -165,7 +165,7 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 // accumulating the partials of tile i+1 - the epilogue is fully overlapped with the main loop.
 constexpr int GROUP_THREADS = 128;
 
-template <int MODE>
+template <int MODE, bool OUT_F32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ UmmaParams p) {
@@ -391,6 +391,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       asm volatile("bar.arrive %0, 256;" ::"r"(4 - group) : "memory");                    // the other group's turn
 
       // ---- epilogue from registers: BN affine, activation, residual, format split, store ----
+      // (kept compact on purpose: the first version of this block was 17k SASS instructions and stalled on
+      //  instruction fetch - profiles/r1_ncu_summary.md)
       const int m = m0 + row;
       if (m >= p.M) continue;
       size_t pix[4];
@@ -410,62 +412,70 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int nb = n0 + c0;
         if (c >= nchunks || nb >= p.Cout) continue;
         float* y = acc[c];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = fmaf(y[i], s_scale[c0 + i], s_scale[p.BN + c0 + i]);
-          if (p.act == ACT_LEAKY) t = t > 0.f ? t : 0.1f * t;
-          else if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
-          y[i] = t;
-        }
         const int nvalid = min(32, p.Cout - nb);
-        if (p.res) {                                        // residual add (DarknetBasicBlockV3), stored in the activation format
-          const int rnp = p.res_dtype == DT_BF16X3 ? 3 : (p.res_dtype == DT_F16X2 ? 2 : 1);
-          const unsigned short* rp = static_cast<const unsigned short*>(p.res) + (size_t)m * p.res_cpitch + p.res_coff + nb;
-          for (int pl = 0; pl < rnp; ++pl) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(rp + (size_t)pl * p.res_plane_stride);
-            const float pw = (p.res_dtype == DT_F16X2 && pl == 1) ? kF16LoScaleInv : 1.f;
-            uint4 u4[4];
+        {
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
+          const float4* sh4 = reinterpret_cast<const float4*>(s_scale + p.BN + c0);
+          const bool leaky = p.act == ACT_LEAKY, relu = p.act == ACT_RELU;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) u4[q] = __ldg(r4 + q);
+          for (int q = 0; q < 8; ++q) {
+            const float4 a = sc4[q], b = sh4[q];
+            const float sc[4] = {a.x, a.y, a.z, a.w}, sh[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t uu[4] = {u4[q].x, u4[q].y, u4[q].z, u4[q].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 f;
-                if (p.res_dtype == DT_F16X2) f = __half22float2(*reinterpret_cast<const __half2*>(&uu[e]));
-                else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uu[e]));
-                y[q * 8 + 2 * e] = fmaf(f.x, pw, y[q * 8 + 2 * e]);
-                y[q * 8 + 2 * e + 1] = fmaf(f.y, pw, y[q * 8 + 2 * e + 1]);
-              }
+            for (int e = 0; e < 4; ++e) {
+              float t = fmaf(y[4 * q + e], sc[e], sh[e]);
+              t = leaky ? fmaxf(t, 0.1f * t) : (relu ? fmaxf(t, 0.f) : t);
+              y[4 * q + e] = t;
             }
           }
         }
-        if (p.out_dtype == DT_F32) {                        // head convs: fp32 NHWC == (B, H*W, A, C)
+        if (OUT_F32) {                                      // head convs: fp32 NHWC == (B, H*W, A, C)
           float* op = static_cast<float*>(p.out) + pix[0] * p.out_cpitch + p.out_coff + nb;
-          if (nvalid == 32 && ((p.out_cpitch | p.out_coff) & 3) == 0) {
+          if (((p.out_cpitch | p.out_coff) & 1) == 0) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(op)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-          } else if (((p.out_cpitch | p.out_coff) & 1) == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2)
+            for (int i = 0; i < 32; i += 2) {
               if (i + 1 < nvalid) *reinterpret_cast<float2*>(op + i) = make_float2(y[i], y[i + 1]);
               else if (i < nvalid) op[i] = y[i];
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (i < nvalid) op[i] = y[i];
           }
         } else {
+          constexpr bool F16 = MODE == 2;
+          if (p.res) {                                      // residual add (DarknetBasicBlockV3), stored in the activation format
+            const unsigned short* rp = static_cast<const unsigned short*>(p.res) + (size_t)m * p.res_cpitch + p.res_coff + nb;
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(rp + (size_t)pl * p.res_plane_stride);
+              const float pw = (F16 && pl == 1) ? kF16LoScaleInv : 1.f;
+              uint4 u4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) u4[q] = __ldg(r4 + q);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t uu[4] = {u4[q].x, u4[q].y, u4[q].z, u4[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f;
+                  if (F16) f = __half22float2(*reinterpret_cast<const __half2*>(&uu[e]));
+                  else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uu[e]));
+                  y[q * 8 + 2 * e] = fmaf(f.x, pw, y[q * 8 + 2 * e]);
+                  y[q * 8 + 2 * e + 1] = fmaf(f.y, pw, y[q * 8 + 2 * e + 1]);
+                }
+              }
+            }
+          }
           // split into the planes of the activation format and store 64 contiguous bytes per plane
-          const int onp = p.out_dtype == DT_BF16X3 ? 3 : (p.out_dtype == DT_F16X2 ? 2 : 1);
-          for (int pl = 0; pl < onp; ++pl) {
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl) {
             uint32_t w[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              float a = y[i], b = y[i + 1];
-              if (p.out_dtype == DT_F16X2) {
-                a = fminf(fmaxf(a, -kF16Max), kF16Max); b = fminf(fmaxf(b, -kF16Max), kF16Max);
+              if (F16) {
+                float a = y[i], b = y[i + 1];
+                if (pl == 0) { a = fminf(fmaxf(a, -kF16Max), kF16Max); b = fminf(fmaxf(b, -kF16Max), kF16Max); }
                 __half2 h = __floats2half2_rn(a, b);
                 w[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
                 if (pl == 0) {
@@ -473,21 +483,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   y[i] = (y[i] - f.x) * kF16LoScale; y[i + 1] = (y[i + 1] - f.y) * kF16LoScale;     // exact: remainder has <= 13 bits
                 }
               } else {
-                float ha = bf16_round(a), hb = bf16_round(b);
+                float ha = bf16_round(y[i]), hb = bf16_round(y[i + 1]);
                 w[i >> 1] = pack_bf16(ha, hb);
-                y[i] = a - ha; y[i + 1] = b - hb;
+                if (pl + 1 < NP) { y[i] -= ha; y[i + 1] -= hb; }
               }
             }
             for (int q = 0; q < npix; ++q) {
-              unsigned short* op = static_cast<unsigned short*>(p.out) + (size_t)pl * p.out_plane_stride + pix[q] * p.out_cpitch + p.out_coff + nb;
-              if (nvalid == 32) {
+              uint4* op = reinterpret_cast<uint4*>(static_cast<unsigned short*>(p.out) + (size_t)pl * p.out_plane_stride +
+                                                   pix[q] * p.out_cpitch + p.out_coff + nb);
 #pragma unroll
-                for (int g = 0; g < 4; ++g) reinterpret_cast<uint4*>(op)[g] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < nvalid) op[i] = (i & 1) ? (unsigned short)(w[i >> 1] >> 16) : (unsigned short)(w[i >> 1] & 0xFFFFu);
-              }
+              for (int g = 0; g < 4; ++g)
+                if (g * 8 < nvalid) op[g] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);   // Cout % 8 == 0
             }
           }
         }
@@ -638,19 +644,23 @@ void umma_release(UmmaConv& u) {
 
 static int g_num_sms = 0;
 
-template <int MODE>
-static int launch_mode(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
+template <int MODE, bool OUT_F32>
+static int launch_mode2(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    YB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    YB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
-  conv_umma_kernel<MODE><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
-                                                                *reinterpret_cast<const CUtensorMap*>(u.map_b), p);
+  conv_umma_kernel<MODE, OUT_F32><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
+                                                                         *reinterpret_cast<const CUtensorMap*>(u.map_b), p);
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
+}
+template <int MODE>
+static int launch_mode(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
+  return p.out_dtype == DT_F32 ? launch_mode2<MODE, true>(u, p, smem_bytes, st) : launch_mode2<MODE, false>(u, p, smem_bytes, st);
 }
 
 int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
@@ -677,7 +687,11 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
   p.b_plane_rows = p.n_tiles_n * p.BN;
   const int stage_bytes = np * (TILE_M * p.bk * 2 + p.BN * p.bk * 2);
   const int aux_bytes = 16 * MAX_STAGES + 128 + 2 * 2 * p.BN * 4 + 64;
-  p.flush = p.bk == 64 ? 2 : 4;             // 8 MMAs of the leading product per partial
+  // 8 MMAs of the leading product per TMEM partial.  Longer partials are ~3 % faster but their truncation bias is
+  // systematic (same sign on every output) and compounds through the layers: flush 8 -> Darknet-53 head error 6.6e-4
+  // instead of 2.9e-4 (profiles/r1_parity_report.txt).  Env YOLO_B200_FLUSH overrides for experiments.
+  p.flush = p.bk == 64 ? 2 : 4;
+  if (const char* fe = getenv("YOLO_B200_FLUSH")) { int f = atoi(fe); if (f >= 1 && f <= 64) p.flush = f; }
   int stages = (SMEM_LIMIT - 1024 - aux_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return fail(YOLO_E_UNSUPPORTED, "umma: tile does not fit two pipeline stages");
@@ -687,7 +701,7 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
   p.out = d.out; p.out_dtype = d.out_dtype; p.out_cpitch = d.out_cpitch; p.out_coff = d.out_coff; p.upsample2 = d.upsample2;
   p.res_plane_stride = d.res_plane_stride;
   p.out_plane_stride = d.out_plane_stride;
-  if (d.out_dtype != DT_F32 && ((d.out_cpitch | d.out_coff) & 7)) return fail(YOLO_E_UNSUPPORTED, "umma: 16-bit output needs 16-byte aligned channel slices");
+  if (d.out_dtype != DT_F32 && (((d.out_cpitch | d.out_coff) & 7) || d.Cout % 8)) return fail(YOLO_E_UNSUPPORTED, "umma: 16-bit output needs 16-byte aligned channel slices and Cout %% 8 == 0");
   if (d.res && ((d.res_cpitch | d.res_coff) & 7)) return fail(YOLO_E_UNSUPPORTED, "umma: residual needs 16-byte aligned channel slices");
   if (d.res && (d.Cout % 32 || d.out_dtype == DT_F32)) return fail(YOLO_E_UNSUPPORTED, "umma: residual needs Cout %% 32 == 0 and a 16-bit activation format");
   const int smem_bytes = 1024 + stages * stage_bytes + aux_bytes;

@@ -571,7 +571,7 @@ extern "C" int yolo_set_workspace(yolo_handle* h, void* device_ptr, size_t bytes
       if (op.in.buf < 0) { op.umma.enabled = false; continue; }
       // epilogue constraints of the tensor-core kernel: 16-byte aligned 16-bit channel slices, 32-column residual chunks
       const bool out16 = op.out.dtype != DT_F32;
-      if ((out16 && ((op.out.cpitch | op.out.coff) & 7)) || (op.has_res && (((op.res.cpitch | op.res.coff) & 7) || op.cout % 32 || !out16))) {
+      if ((out16 && (((op.out.cpitch | op.out.coff) & 7) || op.cout % 8)) || (op.has_res && (((op.res.cpitch | op.res.coff) & 7) || op.cout % 32 || !out16))) {
         op.umma.enabled = false;
         continue;
       }
