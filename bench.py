@@ -165,7 +165,7 @@ def run_ours(args):
             "all_anchors": [[[0.2216, 0.1552], [0.2144, 0.2408], [0.2825, 0.3456]], [[0.3959, 0.2706], [0.3703, 0.4351], [0.5708, 0.4278]],
                             [[0.4345, 0.6063], [0.5584, 0.7174], [0.7448, 0.6772]]],
             "classes": list(range(24)), "use_fp16": False}
-    y = yolo_b200.YOLO(args=None, spec=spec, precision=precision, max_batch=B)
+    y = yolo_b200.YOLO(args=None, spec=spec, precision=precision, max_batch=B, gpu=local)
     # every rank = an independent replica with the same weights (inference shards by batch, no collective)
     y.net.load_params(synth.random_params(y.net.param_shapes(), seed=2024, channels_per_anchor=30))
     rng = np.random.default_rng(1234 + rank)
@@ -242,6 +242,13 @@ def run_ours(args):
             peak_note = (f"{pk_src} bf16 sustained {pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))} TF/s / {passes} "
                          f"tcgen05 16-bit MMA passes per fp32-grade product" if passes > 1 else f"{pk_src} bf16 sustained")
         achieved = B * flops_img / (fwd_ms / 1e3) / 1e12
+        traffic, traffic_note = None, None
+        tp = os.path.join(ROOT, "profiles", f"r1_step_traffic_{precision}.json")
+        if os.path.exists(tp) and B == 32 and S == 416:
+            tj = json.load(open(tp))
+            traffic = tj["conv_launches_dram_bytes_per_step"]
+            traffic_note = ("dram__bytes_read+write summed over the conv launches of one step from a committed ncu capture "
+                            "(profiles/r1_step_traffic_%s.csv), not measured in this run" % precision)
         dec_bytes = B * sum(o.t[0].numel() for o in out) * 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -255,7 +262,8 @@ def run_ours(args):
                     "api": "YOLO.net.forward(data=pinned uint8 NHWC host frames) + YOLO.predict -> numpy"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": None, "kernel": "conv forward (all conv launches of a step)", "algorithmic_flops_per_step": B * flops_img,
+                         "traffic": traffic, "traffic_note": traffic_note,
+                         "kernel": "conv forward (all conv launches of a step)", "algorithmic_flops_per_step": B * flops_img,
                          "avg_forward_ms": fwd_ms, "peak_source": peak_note},
             "roofline_decode": {"bound": "hbm", "achieved": dec_bytes / (dec_ms / 1e3) / 1e9, "peak": float(pk.get("hbm_gbs", 6650.0)),
                                 "unit": "GB/s", "frac": dec_bytes / (dec_ms / 1e3) / 1e9 / float(pk.get("hbm_gbs", 6650.0)),

@@ -611,6 +611,12 @@ extern "C" int yolo_forward(yolo_handle* h, const void* input, int batch, int in
     if (!outputs[i]) return hfail(h, fail(YOLO_E_BADARG, "forward: outputs[%zu] is null", i));
   cudaError_t ce = cudaSetDevice(h->device);
   if (ce != cudaSuccess) return hfail(h, fail(YOLO_E_CUDA, "forward: cudaSetDevice(%d): %s", h->device, cudaGetErrorString(ce)));
+  {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, input) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != h->device)
+      return hfail(h, fail(YOLO_E_BADARG, "forward: input lives on device %d but the handle was created for device %d", pa.device, h->device));
+    cudaGetLastError();
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const int launches0 = g_launches;
   for (auto& op : h->ops) {

@@ -57,9 +57,9 @@ class YOLO:
 
     net_type = "carnet"
 
-    def __init__(self, args=None, spec=None, params=None, precision="fp32", max_batch=1):
+    def __init__(self, args=None, spec=None, params=None, precision="fp32", max_batch=1, gpu=None):
         args = _args(args, gpu="0", mode="video")
-        self.ctx = get_ctx(args.gpu)
+        self.ctx = get_ctx(args.gpu if gpu is None else str(gpu))
         spec = _load_spec(args, spec)
         for key in spec:                                   # car/YOLO.py:58-59
             setattr(self, key, spec[key])
@@ -122,14 +122,14 @@ class CarLPYOLO(YOLO):
 class LicencePlateDetectioin:
     """licence_plate/LP_detection.py: DenseNet pose detector."""
 
-    def __init__(self, args=None, spec=None, params=None, precision="fp32", max_batch=1):
+    def __init__(self, args=None, spec=None, params=None, precision="fp32", max_batch=1, gpu=None):
         args = _args(args, gpu="0", mode="video")
         spec = _load_spec(args, spec)
         for key in spec:                                   # LP_detection.py:106-107
             setattr(self, key, spec[key])
         self.spec = spec
         self.version = getattr(args, "version", None)
-        self.ctx = get_ctx(args.gpu)
+        self.ctx = get_ctx(args.gpu if gpu is None else str(gpu))
         self.num_downsample = len(self.block_config) + 1
         self.net = api.Net("lpdensenet", spec, precision, max_batch, self.ctx[0])
         if params is not None:
