@@ -135,6 +135,42 @@ def test_dk53_416_end_to_end(precision):
     assert abs(y.net.conv_flops_per_image / 1e9 - 113.263) < 1e-2
 
 
+@pytest.mark.parametrize("precision", ["fp16x3"])
+@pytest.mark.parametrize("name,net,spec,B", [
+    ("cfg3 LPDenseNet v2 320x512", "lpdensenet", nets.spec_lp_v2(), 2),                 # licence_plate/v2/spec.yaml
+    ("car/v1 native 320x512", "carnet", nets.spec_v1_native(), 1),                      # car/v1/spec.yaml (6 stages, strides 16/32/64)
+    ("cfg5 car_and_LP Darknet-53 608x608", "carlpnet", nets.spec_dk53((608, 608), 30, True), 1),
+])
+def test_full_size_configs(name, net, spec, B, precision):
+    """The other BASELINE configs at their real sizes (small batch): heads within the noise-aware bound, decoded
+    selections identical to the oracle's."""
+    import yolo_b200
+    params = weights.make_params(net, spec, seed=77, calib_batch=1)
+    x, _ = weights.synthetic_frames(B, spec["size"], seed=99)
+    n, res = _run(net, spec, params, x, precision)
+    ref32 = oracle_outputs(net, spec, params, x)
+    ref64 = oracle_outputs(net, spec, params, x, torch.float64)
+    for i, (a, r32, r64) in enumerate(zip(res, ref32, ref64)):
+        noise_aware_check(a, r32.reshape(a.shape), r64.reshape(a.shape), what=f"{name} out{i}")
+    if net == "lpdensenet":
+        rows, idx = yolo_b200.decode_lp(torch.from_numpy(res[0]).cuda(), 1, spec["LP_r_max"])
+        for b in range(B):
+            orow, oi = decode.predict_LP_single(spec, ref32[0][b:b + 1], return_index=True)
+            assert int(idx[b]) == oi
+            np.testing.assert_allclose(rows[b].cpu().numpy(), orow, rtol=0, atol=1e-4 * max(1.0, np.abs(orow).max()))
+        return
+    rows, idx = yolo_b200.decode_top1(spec, [torch.from_numpy(r).cuda() for r in res[:3]])
+    orows, oidx = decode.predict(spec, ref32[:3], return_index=True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oidx)
+    rows64 = decode.predict(spec, [r.astype(np.float32) for r in ref64[:3]])
+    noise_aware_check(rows.cpu().numpy()[:, :5], orows[:, :5], rows64[:, :5], what=f"{name} score+bbox")
+    if net == "carlpnet":
+        lrows, lidx = yolo_b200.decode_lp(torch.from_numpy(res[3]).cuda(), 0, spec["LP_r_max"])
+        olr, oli = decode.predict_LP_batch(spec, ref32[3], return_index=True)
+        np.testing.assert_array_equal(lidx.cpu().numpy(), oli)
+        assert abs(float(lrows[0, 0]) - float(olr[0, 0])) <= 1e-3      # LP branch: 31 chained convs, oracle noise ~1e-3
+
+
 def test_bf16_fast_mode_reported_tolerance():
     """Single-pass bf16 (tcgen05) is the fast mode: NOT parity grade.  With synthetic (non-contractive) weights its
     error is measured and bounded loosely here; structural bugs (wrong tap / swizzle / plane) would be O(1-10)."""

@@ -56,6 +56,7 @@ struct UmmaParams {
   int b_plane_rows;                         // weight rows per plane (= padded Cout)
   int stages;
   int flush;                                // k-blocks per TMEM partial sum (two-level accumulation)
+  int dual;                                 // 1: CTA tile = two M tiles sharing the weight tile
   // epilogue
   const float* scale;  const float* shift;  int act;
   const void* res;  int res_dtype, res_cpitch, res_coff;  long long res_plane_stride;   // elements
@@ -165,10 +166,15 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 // accumulating the partials of tile i+1 - the epilogue is fully overlapped with the main loop.
 constexpr int GROUP_THREADS = 128;
 
-template <int MODE, bool OUT_F32>
+// DUAL: the CTA tile is 256 x BN = two 128-row M tiles that share every weight tile in shared memory (the main loop
+// is paced by the TMA ingest rate, ~3 cycles per 128-byte row: sharing B cuts the rows per MMA from 512 to 384).
+// Group g then owns M tile g of every pair, with its own partial/correction buffers and barriers.
+template <int MODE, bool OUT_F32, bool DUAL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ UmmaParams p) {
+  static_assert(!DUAL || MODE != 0, "dual-M tiles need the correction-buffer TMEM layout");
+  constexpr int NMT = DUAL ? 2 : 1;                                // M tiles per CTA tile
   constexpr int NP = MODE == 0 ? 1 : (MODE == 1 ? 3 : 2);          // operand planes
   constexpr int N_PAIRS = MODE == 0 ? 1 : (MODE == 1 ? 6 : 3);     // plane pairs multiplied per k-step
   constexpr bool HAS_CORR = MODE != 0;
@@ -179,7 +185,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int b_tile_bytes = p.BN * p.bk * 2;
-  const int stage_bytes = NP * (A_TILE_BYTES + b_tile_bytes);
+  const int stage_bytes = NP * (NMT * A_TILE_BYTES + b_tile_bytes);
   const uint32_t tiles_end = smem_base + p.stages * stage_bytes;
   unsigned char* aux = smem_gen + (size_t)p.stages * stage_bytes;
   // barrier layout (8 bytes each): full[8] empty[8] pfull[2] pempty[2] cfull[2] cempty[2]
@@ -228,10 +234,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int HoWo = p.Ho * p.Wo;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
-        const int m0 = mt * TILE_M, n0 = nt * p.BN;
-        const int img = m0 / HoWo, rem = m0 - img * HoWo;
-        const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
-        const int bw = ow * p.stride - p.pad, bh = oh * p.stride - p.pad;     // receptive-field origin of the first pixel
+        const int n0 = nt * p.BN;
+        int img[NMT], bw[NMT], bh[NMT];
+#pragma unroll
+        for (int h = 0; h < NMT; ++h) {
+          const int m0 = (mt * NMT + h) * TILE_M;
+          img[h] = m0 / HoWo;
+          const int rem = m0 - img[h] * HoWo;
+          const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+          bw[h] = ow * p.stride - p.pad; bh[h] = oh * p.stride - p.pad;          // receptive-field origin of the first pixel
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
           const int r = tap / p.kw, s = tap - r * p.kw;
@@ -239,11 +251,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t full = bar_full + 8 * stage;
           mbar_expect_tx(full, (uint32_t)stage_bytes);
           const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + NP * A_TILE_BYTES;
+          const uint32_t sb = sa + NMT * NP * A_TILE_BYTES;
 #pragma unroll
           for (int pl = 0; pl < NP; ++pl) {
-            tma_load_im2col_4d(sa + pl * A_TILE_BYTES, &map_a, full, p.in_coff + cb * p.bk, bw, bh, img + pl * p.a_plane_n,
-                               (uint16_t)s, (uint16_t)r);
+#pragma unroll
+            for (int h = 0; h < NMT; ++h)
+              tma_load_im2col_4d(sa + (h * NP + pl) * A_TILE_BYTES, &map_a, full, p.in_coff + cb * p.bk, bw[h], bh[h],
+                                 img[h] + pl * p.a_plane_n, (uint16_t)s, (uint16_t)r);
             tma_load_2d(sb + pl * b_tile_bytes, &map_b, full, kb * p.bk, n0 + pl * p.b_plane_rows);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -259,57 +273,91 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t phase = 0;
       int it = 0;
       uint32_t pcount = 0;                                                     // partial buffers handed out so far
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int cbuf = it & 1;
-        if (HAS_CORR) {
-          mbar_wait(bar_cempty + 8 * cbuf, (((uint32_t)it >> 1) & 1) ^ 1);     // correction buffer drained (tile it-2)
-          tc_fence_after();
-        }
-        const uint32_t tmem_corr = tmem_base + (2 + cbuf) * acc_stride;
-        uint32_t corr_written = 0;
-        uint32_t tmem_main = 0;
-        uint32_t main_written = 0;
-        int pbuf = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-          if (kb % p.flush == 0) {                                             // start a new partial sum
-            pbuf = pcount & 1;
-            mbar_wait(bar_pempty + 8 * pbuf, ((pcount >> 1) & 1) ^ 1);
-            tc_fence_after();
-            tmem_main = tmem_base + pbuf * acc_stride;
-            main_written = 0;
-          }
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + NP * A_TILE_BYTES;
+      auto issue_pairs = [&](uint32_t sa_tile, uint32_t sb, uint32_t tmem_main, uint32_t tmem_corr, uint32_t& main_written,
+                             uint32_t& corr_written) {
 #pragma unroll
-          for (int pair = 0; pair < N_PAIRS; ++pair) {
-            // pair 0 = leading product (plane 0 x plane 0) -> partial buffer; the rest -> correction accumulator
-            constexpr int PA6[6] = {0, 0, 1, 0, 1, 2}, PB6[6] = {0, 1, 0, 2, 1, 0};
-            constexpr int PA3[3] = {0, 0, 1}, PB3[3] = {0, 1, 0};
-            const int pa = MODE == 0 ? 0 : (MODE == 1 ? PA6[pair] : PA3[pair]);
-            const int pb = MODE == 0 ? 0 : (MODE == 1 ? PB6[pair] : PB3[pair]);
-            const uint64_t adesc = make_smem_desc(sa + pa * A_TILE_BYTES, row_bytes);
-            const uint64_t bdesc = make_smem_desc(sb + pb * b_tile_bytes, row_bytes);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-              if (pair == 0) {
-                umma_bf16(tmem_main, adesc + koff, bdesc + koff, idesc, main_written);
-                main_written = 1;
-              } else {
-                umma_bf16(tmem_corr, adesc + koff, bdesc + koff, idesc, corr_written);
-                corr_written = 1;
-              }
+        for (int pair = 0; pair < N_PAIRS; ++pair) {
+          // pair 0 = leading product (plane 0 x plane 0) -> partial buffer; the rest -> correction accumulator
+          constexpr int PA6[6] = {0, 0, 1, 0, 1, 2}, PB6[6] = {0, 1, 0, 2, 1, 0};
+          constexpr int PA3[3] = {0, 0, 1}, PB3[3] = {0, 1, 0};
+          const int pa = MODE == 0 ? 0 : (MODE == 1 ? PA6[pair] : PA3[pair]);
+          const int pb = MODE == 0 ? 0 : (MODE == 1 ? PB6[pair] : PB3[pair]);
+          const uint64_t adesc = make_smem_desc(sa_tile + pa * A_TILE_BYTES, row_bytes);
+          const uint64_t bdesc = make_smem_desc(sb + pb * b_tile_bytes, row_bytes);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+            if (pair == 0) {
+              umma_bf16(tmem_main, adesc + koff, bdesc + koff, idesc, main_written);
+              main_written = 1;
+            } else {
+              umma_bf16(tmem_corr, adesc + koff, bdesc + koff, idesc, corr_written);
+              corr_written = 1;
             }
           }
-          umma_commit(bar_empty + 8 * stage);                                 // frees the smem stage when the MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          if ((kb + 1) % p.flush == 0 || kb + 1 == nkb) {                      // partial complete -> accumulation warps
-            umma_commit(bar_pfull + 8 * pbuf);
-            ++pcount;
-          }
         }
-        if (HAS_CORR) umma_commit(bar_cfull + 8 * cbuf);
+      };
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        if (!DUAL) {
+          const int cbuf = it & 1;
+          if (HAS_CORR) {
+            mbar_wait(bar_cempty + 8 * cbuf, (((uint32_t)it >> 1) & 1) ^ 1);   // correction buffer drained (tile it-2)
+            tc_fence_after();
+          }
+          const uint32_t tmem_corr = tmem_base + (2 + cbuf) * acc_stride;
+          uint32_t corr_written = 0, tmem_main = 0, main_written = 0;
+          int pbuf = 0;
+          for (int kb = 0; kb < nkb; ++kb) {
+            if (kb % p.flush == 0) {                                           // start a new partial sum
+              pbuf = pcount & 1;
+              mbar_wait(bar_pempty + 8 * pbuf, ((pcount >> 1) & 1) ^ 1);
+              tc_fence_after();
+              tmem_main = tmem_base + pbuf * acc_stride;
+              main_written = 0;
+            }
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            issue_pairs(sa, sa + NP * A_TILE_BYTES, tmem_main, tmem_corr, main_written, corr_written);
+            umma_commit(bar_empty + 8 * stage);                               // frees the smem stage when the MMAs retire
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if ((kb + 1) % p.flush == 0 || kb + 1 == nkb) {                    // partial complete -> accumulation warps
+              umma_commit(bar_pfull + 8 * pbuf);
+              ++pcount;
+            }
+          }
+          if (HAS_CORR) umma_commit(bar_cfull + 8 * cbuf);
+        } else {
+          // two M tiles: partial buffer h / correction buffer h belong to M tile h (and to epilogue group h)
+          uint32_t corr_written[2] = {0, 0}, main_written[2] = {0, 0};
+          for (int kb = 0; kb < nkb; ++kb) {
+            const bool new_part = kb % p.flush == 0;
+            const bool end_part = (kb + 1) % p.flush == 0 || kb + 1 == nkb;
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            const uint32_t sb = sa + NMT * NP * A_TILE_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (kb == 0) {
+                mbar_wait(bar_cempty + 8 * h, ((uint32_t)it & 1) ^ 1);        // group h has read the previous pair's correction
+                tc_fence_after();
+              }
+              if (new_part) {
+                mbar_wait(bar_pempty + 8 * h, (pcount & 1) ^ 1);              // group h has drained the previous partial
+                tc_fence_after();
+                main_written[h] = 0;
+              }
+              issue_pairs(sa + h * NP * A_TILE_BYTES, sb, tmem_base + h * acc_stride, tmem_base + (2 + h) * acc_stride, main_written[h],
+                          corr_written[h]);
+              if (end_part) umma_commit(bar_pfull + 8 * h);
+            }
+            umma_commit(bar_empty + 8 * stage);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if (end_part) ++pcount;
+          }
+          umma_commit(bar_cfull + 8 * 0);
+          umma_commit(bar_cfull + 8 * 1);
+        }
       }
     }
   } else {
@@ -322,14 +370,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float* s_scale = s_scale_all + group * 2 * p.BN;
     const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
     const int nchunks = (p.BN + 31) >> 5;
-    int it = group;
+    int it = DUAL ? 0 : group;
     // Accumulation turns.  An mbarrier parity wait can only tell "this phase" from "the previous one", so a group must
     // not start waiting for its partials before the other group has consumed all of the preceding tile's partials:
     // named barriers 3/4 pass the turn (FA3-style ping-pong); group 1 donates the first turn to group 0.
-    if (group == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");
-    for (int tile = blockIdx.x + group * gridDim.x; tile < p.n_tiles; tile += 2 * gridDim.x, it += 2) {
+    if (!DUAL && group == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");
+    for (int tile = blockIdx.x + (DUAL ? 0 : group * (int)gridDim.x); tile < p.n_tiles;
+         tile += (DUAL ? 1 : 2) * gridDim.x, it += (DUAL ? 1 : 2)) {
       const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
-      const int m0 = mt * TILE_M, n0 = nt * p.BN;
+      const int m0 = (DUAL ? mt * 2 + group : mt) * TILE_M, n0 = nt * p.BN;
       // stage scale/shift of this tile's columns (the group's previous tile is completely finished here)
       asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       for (int i = et; i < p.BN; i += GROUP_THREADS) {
@@ -346,11 +395,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int i = 0; i < 32; ++i) acc[c][i] = 0.f;
 
       // ---- level 2: add the TMEM partial sums into registers (round-to-nearest) ----
-      asm volatile("bar.sync %0, 256;" ::"r"(3 + group) : "memory");                      // my turn
+      if (!DUAL) asm volatile("bar.sync %0, 256;" ::"r"(3 + group) : "memory");           // my turn
       uint32_t pc = (uint32_t)it * (uint32_t)npart;
       for (int part = 0; part < npart; ++part, ++pc) {
-        const int pbuf = pc & 1;
-        mbar_wait(bar_pfull + 8 * pbuf, (pc >> 1) & 1);
+        const int pbuf = DUAL ? group : (int)(pc & 1);
+        mbar_wait(bar_pfull + 8 * pbuf, DUAL ? (pc & 1) : ((pc >> 1) & 1));
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_addr + pbuf * acc_stride;
 #pragma unroll
@@ -368,8 +417,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) mbar_arrive(bar_pempty + 8 * pbuf);
       }
       if (HAS_CORR) {
-        const int cbuf = it & 1;
-        mbar_wait(bar_cfull + 8 * cbuf, ((uint32_t)it >> 1) & 1);
+        const int cbuf = DUAL ? group : (it & 1);
+        mbar_wait(bar_cfull + 8 * cbuf, DUAL ? ((uint32_t)it & 1) : (((uint32_t)it >> 1) & 1));
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_addr + (2 + cbuf) * acc_stride;
         const float cw = MODE == 2 ? kF16LoScaleInv : 1.f;
@@ -388,7 +437,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) mbar_arrive(bar_cempty + 8 * cbuf);
       }
 
-      asm volatile("bar.arrive %0, 256;" ::"r"(4 - group) : "memory");                    // the other group's turn
+      if (!DUAL) asm volatile("bar.arrive %0, 256;" ::"r"(4 - group) : "memory");         // the other group's turn
 
       // ---- epilogue from registers: BN affine, activation, residual, format split, store ----
       // (kept compact on purpose: the first version of this block was 17k SASS instructions and stalled on
@@ -644,23 +693,26 @@ void umma_release(UmmaConv& u) {
 
 static int g_num_sms = 0;
 
-template <int MODE, bool OUT_F32>
-static int launch_mode2(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
+template <int MODE, bool OUT_F32, bool DUAL>
+static int launch_mode3(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    YB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    YB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE, OUT_F32, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
   const int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
-  conv_umma_kernel<MODE, OUT_F32><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
-                                                                         *reinterpret_cast<const CUtensorMap*>(u.map_b), p);
+  conv_umma_kernel<MODE, OUT_F32, DUAL><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
+                                                                               *reinterpret_cast<const CUtensorMap*>(u.map_b), p);
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
 }
 template <int MODE>
 static int launch_mode(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
-  return p.out_dtype == DT_F32 ? launch_mode2<MODE, true>(u, p, smem_bytes, st) : launch_mode2<MODE, false>(u, p, smem_bytes, st);
+  if constexpr (MODE == 2) {
+    if (p.dual) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, true>(u, p, smem_bytes, st) : launch_mode3<MODE, false, true>(u, p, smem_bytes, st);
+  }
+  return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, false>(u, p, smem_bytes, st) : launch_mode3<MODE, false, false>(u, p, smem_bytes, st);
 }
 
 int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
@@ -685,7 +737,15 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
   p.in_coff = d.in_coff;
   p.a_plane_n = u.max_batch;
   p.b_plane_rows = p.n_tiles_n * p.BN;
-  const int stage_bytes = np * (TILE_M * p.bk * 2 + p.BN * p.bk * 2);
+  // dual-M tiles (fp16x3 only, EXPERIMENTAL, off by default; YOLO_B200_DUAL=1 enables): sharing the weight tile between two
+  // M tiles cuts the TMA bytes per MMA by 25 % but measured no gain (head 3x3: 753 vs 760 us) - the main loop is bound
+  // by SHARED-MEMORY bandwidth (MMA operand reads + TMA fill = 213 B/clk at 128x128 vs the 128 B/clk port), which this
+  // does not change enough; see profiles/r1_ncu_summary.md.  The real fix is cta_group::2 with 256x256 tiles.
+  const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
+  p.dual = 0;
+  if (const char* de = getenv("YOLO_B200_DUAL")) p.dual = (de[0] == '1' && mode_of(u.precision) == 2 && m_tiles >= 2) ? 1 : 0;
+  if (p.dual) p.n_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
+  const int stage_bytes = np * ((p.dual ? 2 : 1) * TILE_M * p.bk * 2 + p.BN * p.bk * 2);
   const int aux_bytes = 16 * MAX_STAGES + 128 + 2 * 2 * p.BN * 4 + 64;
   // 8 MMAs of the leading product per TMEM partial.  Longer partials are ~3 % faster but their truncation bias is
   // systematic (same sign on every output) and compounds through the layers: flush 8 -> Darknet-53 head error 6.6e-4
