@@ -270,6 +270,7 @@ def run_ours(args):
                                 "algorithmic_bytes_per_step": dec_bytes, "avg_decode_ms": dec_ms, "peak_source": pk_src,
                                 "note": "heads were just written by the head convs (L2-resident); launch-latency bound at this size"},
             "clocks": clocks, "wall_s": wall,
+            "step_ms_each": [round(ev[3 * i].elapsed_time(ev[3 * i + 3]), 3) for i in range(args.steps)],
         }
         if world == 1 and not args.no_cpu_baseline:
             del y

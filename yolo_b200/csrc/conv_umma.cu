@@ -56,7 +56,10 @@ struct UmmaParams {
   int b_plane_rows;                         // weight rows per plane (= padded Cout)
   int stages;
   int flush;                                // k-blocks per TMEM partial sum (two-level accumulation)
-  int dual;                                 // 1: CTA tile = two M tiles sharing the weight tile
+  int dual;                                 // 1: CTA tile = two M tiles sharing the weight tile; 2: cta_group::2 pair
+  int dbg_pairs;                            // >0: issue only the first n plane pairs (timing experiments; wrong results)
+  int a_tiled;                              // 1x1/s1/p0: activations are a plain [pixels][channels] matrix -> tiled TMA, not im2col
+  long long a_plane_rows;                   // pixel rows per plane in that matrix (= max_batch*H*W)
   // epilogue
   const float* scale;  const float* shift;  int act;
   const void* res;  int res_dtype, res_cpitch, res_coff;  long long res_plane_stride;   // elements
@@ -101,6 +104,46 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* map
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
 }
+// ---- 2-CTA (cta_group::2) variants: the pair's leader (cluster rank 0) owns the `full` barriers and issues the MMAs ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t saddr) {          // same smem offset in CTA rank 0 (shared::cluster address)
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const void* map, uint32_t bar_rank0, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar_rank0), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d(uint32_t dst, const void* map, uint32_t bar_rank0, int c, int w, int h, int n,
+                                                    uint16_t off_w, uint16_t off_h) {
+  asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+               ::"r"(dst), "l"(map), "r"(bar_rank0), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {            // arrive on the same barrier offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const void* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -117,9 +160,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes
   return d;
 }
 // kind::f16 instruction descriptor: (bf16 | fp16) x same -> fp32, both operands K-major, M = 128.
-__device__ __forceinline__ uint32_t make_idesc(int n, bool fp16) {
+__device__ __forceinline__ uint32_t make_idesc(int n, bool fp16, int m = TILE_M) {
   const uint32_t fmt = fp16 ? 0u : 1u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -169,12 +212,22 @@ constexpr int GROUP_THREADS = 128;
 // DUAL: the CTA tile is 256 x BN = two 128-row M tiles that share every weight tile in shared memory (the main loop
 // is paced by the TMA ingest rate, ~3 cycles per 128-byte row: sharing B cuts the rows per MMA from 512 to 384).
 // Group g then owns M tile g of every pair, with its own partial/correction buffers and barriers.
-template <int MODE, bool OUT_F32, bool DUAL>
+// PAIR (KIND 2): two CTAs of a cluster form one 256 x BN tile with tcgen05 cta_group::2: each CTA stages its own 128
+// rows of A and HALF of the weight tile, the leader issues M=256 MMAs that read both halves, and each CTA keeps the
+// accumulators of its own 128 rows in its own TMEM.  Shared-memory traffic per MMA drops from 8 KB to 6 KB and the
+// TMA fill from 64 KB to 48 KB per k-block (213 -> 156 B/clk against the 128 B/clk port).
+template <int MODE, bool OUT_F32, int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ UmmaParams p) {
-  static_assert(!DUAL || MODE != 0, "dual-M tiles need the correction-buffer TMEM layout");
-  constexpr int NMT = DUAL ? 2 : 1;                                // M tiles per CTA tile
+  // KIND 0: one 128 x BN tile per CTA.   KIND 1: two M tiles per CTA sharing the weight tile (halves along M).
+  // KIND 2: CTA pair, 256 x BN.          KIND 3: CTA pair, 256 x 2BN: two N tiles sharing the activation tiles (halves along N).
+  // "DUAL" = the per-half protocol: epilogue group g owns half g (its own partial/correction buffer and barriers).
+  constexpr bool DUAL = KIND == 1 || KIND == 3, PAIR = KIND == 2 || KIND == 3;
+  constexpr bool HALF_M = KIND == 1, HALF_N = KIND == 3;
+  static_assert(!DUAL || MODE != 0, "dual tiles need the correction-buffer TMEM layout");
+  constexpr int NMT = HALF_M ? 2 : 1;                              // A (activation) tiles per stage
+  constexpr int NBT = HALF_N ? 2 : 1;                              // B (weight) tiles per stage
   constexpr int NP = MODE == 0 ? 1 : (MODE == 1 ? 3 : 2);          // operand planes
   constexpr int N_PAIRS = MODE == 0 ? 1 : (MODE == 1 ? 6 : 3);     // plane pairs multiplied per k-step
   constexpr bool HAS_CORR = MODE != 0;
@@ -184,8 +237,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // carve: [stages][NP A tiles | NP B tiles] then barriers, tmem pointer, scale/shift staging (one copy per group)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int b_tile_bytes = p.BN * p.bk * 2;
-  const int stage_bytes = NP * (NMT * A_TILE_BYTES + b_tile_bytes);
+  const int b_rows = PAIR ? p.BN / 2 : p.BN;                        // weight rows staged by this CTA
+  const int b_tile_bytes = b_rows * p.bk * 2;
+  const int stage_bytes = NP * (NMT * A_TILE_BYTES + NBT * b_tile_bytes);
   const uint32_t tiles_end = smem_base + p.stages * stage_bytes;
   unsigned char* aux = smem_gen + (size_t)p.stages * stage_bytes;
   // barrier layout (8 bytes each): full[8] empty[8] pfull[2] pempty[2] cfull[2] cempty[2]
@@ -196,6 +250,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   float* s_scale_all = reinterpret_cast<float*>(aux + 16 * MAX_STAGES + 128);      // [group][2][BN]: scale, shift
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // persistent scheduling unit (CTA or CTA pair)
+  const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // TMEM: two partial buffers for the leading product + two correction buffers (tile parity), each `acc_stride` columns
   const int acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : 128);
   const int tmem_cols = HAS_CORR ? 4 * acc_stride : (2 * acc_stride < 32 ? 32 : 2 * acc_stride);
@@ -211,18 +268,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_pfull + 8 * b, 1);
-      mbar_init(bar_pempty + 8 * b, GROUP_THREADS / 32);
+      mbar_init(bar_pempty + 8 * b, (PAIR ? 2 : 1) * GROUP_THREADS / 32);      // PAIR: the leader collects both CTAs' groups
       mbar_init(bar_cfull + 8 * b, 1);
-      mbar_init(bar_cempty + 8 * b, GROUP_THREADS / 32);
+      mbar_init(bar_cempty + 8 * b, (PAIR ? 2 : 1) * GROUP_THREADS / 32);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // barrier inits visible to the peer before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -232,13 +294,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       const int HoWo = p.Ho * p.Wo;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tile = sched_id; tile < p.n_tiles; tile += sched_n) {
         const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
-        const int n0 = nt * p.BN;
+        const int n0 = nt * NBT * p.BN + (PAIR ? (int)cta_rank * b_rows : 0);   // HALF_N: N tile h starts at n0 + h*BN
         int img[NMT], bw[NMT], bh[NMT];
 #pragma unroll
         for (int h = 0; h < NMT; ++h) {
-          const int m0 = (mt * NMT + h) * TILE_M;
+          const int m0 = (PAIR ? mt * 2 + (int)cta_rank : mt * NMT + h) * TILE_M;
           img[h] = m0 / HoWo;
           const int rem = m0 - img[h] * HoWo;
           const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
@@ -248,17 +310,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
           const int r = tap / p.kw, s = tap - r * p.kw;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t full = bar_full + 8 * stage;
-          mbar_expect_tx(full, (uint32_t)stage_bytes);
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = sa + NMT * NP * A_TILE_BYTES;
+          if (PAIR) {
+            // both CTAs' bytes complete on the LEADER's full barrier, which the leader arms for 2 x stage_bytes
+            const uint32_t full0 = mapa_rank0(bar_full + 8 * stage);
+            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * (uint32_t)stage_bytes);
 #pragma unroll
-          for (int pl = 0; pl < NP; ++pl) {
+            for (int pl = 0; pl < NP; ++pl) {
+              tma2_load_im2col_4d(sa + pl * A_TILE_BYTES, &map_a, full0, p.in_coff + cb * p.bk, bw[0], bh[0], img[0] + pl * p.a_plane_n,
+                                  (uint16_t)s, (uint16_t)r);
 #pragma unroll
-            for (int h = 0; h < NMT; ++h)
-              tma_load_im2col_4d(sa + (h * NP + pl) * A_TILE_BYTES, &map_a, full, p.in_coff + cb * p.bk, bw[h], bh[h],
-                                 img[h] + pl * p.a_plane_n, (uint16_t)s, (uint16_t)r);
-            tma_load_2d(sb + pl * b_tile_bytes, &map_b, full, kb * p.bk, n0 + pl * p.b_plane_rows);
+              for (int h = 0; h < NBT; ++h)
+                tma2_load_2d(sb + (h * NP + pl) * b_tile_bytes, &map_b, full0, kb * p.bk, n0 + h * p.BN + pl * p.b_plane_rows);
+            }
+          } else {
+            const uint32_t full = bar_full + 8 * stage;
+            mbar_expect_tx(full, (uint32_t)stage_bytes);
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) {
+#pragma unroll
+              for (int h = 0; h < NMT; ++h) {
+                if (p.a_tiled)
+                  tma_load_2d(sa + (h * NP + pl) * A_TILE_BYTES, &map_a, full, p.in_coff + cb * p.bk,
+                              (int)((mt * NMT + h) * TILE_M + pl * p.a_plane_rows));
+                else
+                  tma_load_im2col_4d(sa + (h * NP + pl) * A_TILE_BYTES, &map_a, full, p.in_coff + cb * p.bk, bw[h], bh[h],
+                                     img[h] + pl * p.a_plane_n, (uint16_t)s, (uint16_t)r);
+              }
+              tma_load_2d(sb + pl * b_tile_bytes, &map_b, full, kb * p.bk, n0 + pl * p.b_plane_rows);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -266,8 +347,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.BN, MODE == 2);
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = make_idesc(p.BN, MODE == 2, PAIR ? 256 : TILE_M);
       const int ksteps = p.bk / UMMA_K;
       int stage = 0;
       uint32_t phase = 0;
@@ -277,6 +358,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                              uint32_t& corr_written) {
 #pragma unroll
         for (int pair = 0; pair < N_PAIRS; ++pair) {
+          if (p.dbg_pairs > 0 && pair >= p.dbg_pairs) break;
           // pair 0 = leading product (plane 0 x plane 0) -> partial buffer; the rest -> correction accumulator
           constexpr int PA6[6] = {0, 0, 1, 0, 1, 2}, PB6[6] = {0, 1, 0, 2, 1, 0};
           constexpr int PA3[3] = {0, 0, 1}, PB3[3] = {0, 1, 0};
@@ -287,16 +369,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
             if (pair == 0) {
-              umma_bf16(tmem_main, adesc + koff, bdesc + koff, idesc, main_written);
+              if (PAIR) umma2_bf16(tmem_main, adesc + koff, bdesc + koff, idesc, main_written);
+              else umma_bf16(tmem_main, adesc + koff, bdesc + koff, idesc, main_written);
               main_written = 1;
             } else {
-              umma_bf16(tmem_corr, adesc + koff, bdesc + koff, idesc, corr_written);
+              if (PAIR) umma2_bf16(tmem_corr, adesc + koff, bdesc + koff, idesc, corr_written);
+              else umma_bf16(tmem_corr, adesc + koff, bdesc + koff, idesc, corr_written);
               corr_written = 1;
             }
           }
         }
       };
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      auto commit = [&](uint32_t bar) { if (PAIR) umma2_commit_mc(bar); else umma_commit(bar); };
+      for (int tile = sched_id; tile < p.n_tiles; tile += sched_n, ++it) {
         if (!DUAL) {
           const int cbuf = it & 1;
           if (HAS_CORR) {
@@ -318,14 +403,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_fence_after();
             const uint32_t sa = smem_base + stage * stage_bytes;
             issue_pairs(sa, sa + NP * A_TILE_BYTES, tmem_main, tmem_corr, main_written, corr_written);
-            umma_commit(bar_empty + 8 * stage);                               // frees the smem stage when the MMAs retire
+            commit(bar_empty + 8 * stage);                                    // frees the smem stage (in both CTAs) when the MMAs retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
             if ((kb + 1) % p.flush == 0 || kb + 1 == nkb) {                    // partial complete -> accumulation warps
-              umma_commit(bar_pfull + 8 * pbuf);
+              commit(bar_pfull + 8 * pbuf);
               ++pcount;
             }
           }
-          if (HAS_CORR) umma_commit(bar_cfull + 8 * cbuf);
+          if (HAS_CORR) commit(bar_cfull + 8 * cbuf);
         } else {
           // two M tiles: partial buffer h / correction buffer h belong to M tile h (and to epilogue group h)
           uint32_t corr_written[2] = {0, 0}, main_written[2] = {0, 0};
@@ -347,16 +432,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 tc_fence_after();
                 main_written[h] = 0;
               }
-              issue_pairs(sa + h * NP * A_TILE_BYTES, sb, tmem_base + h * acc_stride, tmem_base + (2 + h) * acc_stride, main_written[h],
-                          corr_written[h]);
-              if (end_part) umma_commit(bar_pfull + 8 * h);
+              issue_pairs(sa + (HALF_M ? h : 0) * NP * A_TILE_BYTES, sb + (HALF_N ? h : 0) * NP * b_tile_bytes, tmem_base + h * acc_stride,
+                          tmem_base + (2 + h) * acc_stride, main_written[h], corr_written[h]);
+              if (end_part) commit(bar_pfull + 8 * h);
             }
-            umma_commit(bar_empty + 8 * stage);
+            commit(bar_empty + 8 * stage);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
             if (end_part) ++pcount;
           }
-          umma_commit(bar_cfull + 8 * 0);
-          umma_commit(bar_cfull + 8 * 1);
+          commit(bar_cfull + 8 * 0);
+          commit(bar_cfull + 8 * 1);
         }
       }
     }
@@ -375,10 +460,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // not start waiting for its partials before the other group has consumed all of the preceding tile's partials:
     // named barriers 3/4 pass the turn (FA3-style ping-pong); group 1 donates the first turn to group 0.
     if (!DUAL && group == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");
-    for (int tile = blockIdx.x + (DUAL ? 0 : group * (int)gridDim.x); tile < p.n_tiles;
-         tile += (DUAL ? 1 : 2) * gridDim.x, it += (DUAL ? 1 : 2)) {
+    for (int tile = sched_id + (DUAL ? 0 : group * sched_n); tile < p.n_tiles; tile += (DUAL ? 1 : 2) * sched_n, it += (DUAL ? 1 : 2)) {
       const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
-      const int m0 = (DUAL ? mt * 2 + group : mt) * TILE_M, n0 = nt * p.BN;
+      const int m0 = (HALF_M ? mt * 2 + group : (PAIR ? mt * 2 + (int)cta_rank : mt)) * TILE_M;
+      const int n0 = (HALF_N ? nt * 2 + group : nt) * p.BN;
       // stage scale/shift of this tile's columns (the group's previous tile is completely finished here)
       asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       for (int i = et; i < p.BN; i += GROUP_THREADS) {
@@ -414,7 +499,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_pempty + 8 * pbuf);
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_rank0(bar_pempty + 8 * pbuf)); else mbar_arrive(bar_pempty + 8 * pbuf); }
       }
       if (HAS_CORR) {
         const int cbuf = DUAL ? group : (it & 1);
@@ -434,7 +519,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_cempty + 8 * cbuf);
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_rank0(bar_cempty + 8 * cbuf)); else mbar_arrive(bar_cempty + 8 * cbuf); }
       }
 
       if (!DUAL) asm volatile("bar.arrive %0, 256;" ::"r"(4 - group) : "memory");         // the other group's turn
@@ -551,10 +636,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // PAIR: the peer may still be arriving on / reading through this CTA
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -657,6 +743,13 @@ int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int co
   CUresult cr = g_encode_tiled(reinterpret_cast<CUtensorMap*>(u.map_b), dt, 2, u.w_packed, gdim, gstr, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(YOLO_E_CUDA, "cuTensorMapEncodeTiled(weights %dx%zu) failed: %d", np * rows, K, (int)cr);
+  u.has_map_b2 = false;
+  if (u.bn_tile % 32 == 0) {                               // half-height box for the 2-CTA path (each CTA stages BN/2 weight rows)
+    cuuint32_t box2[2] = {(cuuint32_t)u.bk, (cuuint32_t)(u.bn_tile / 2)};
+    cr = g_encode_tiled(reinterpret_cast<CUtensorMap*>(u.map_b2), dt, 2, u.w_packed, gdim, gstr, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    u.has_map_b2 = cr == CUDA_SUCCESS;
+  }
   u.eligible = true;
   return YOLO_OK;
 }
@@ -671,6 +764,24 @@ int umma_build_maps(UmmaConv& u, void* in_base, int max_batch, int H, int W, int
   (void)C; (void)coff;
   const CUtensorMapDataType dt = u.precision == YOLO_PREC_FP16X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapSwizzle sw = u.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  u.a_tiled = false;
+  const char* te = getenv("YOLO_B200_A_TILED");
+  if (u.kh == 1 && u.stride == 1 && u.pad == 0 && !(te && te[0] == '0')) {
+    // 1x1 convolution: A is the plain row-major matrix [planes*max_batch*H*W][cpitch] -> tiled map
+    cuuint64_t rows = (cuuint64_t)np * max_batch * H * W;
+    cuuint64_t gd[2] = {(cuuint64_t)cpitch, rows};
+    cuuint64_t gs[1] = {(cuuint64_t)cpitch * 2};
+    cuuint32_t bx[2] = {(cuuint32_t)u.bk, (cuuint32_t)TILE_M};
+    cuuint32_t es[2] = {1, 1};
+    CUresult cr2 = g_encode_tiled(reinterpret_cast<CUtensorMap*>(u.map_a), dt, 2, in_base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr2 != CUDA_SUCCESS) return fail(YOLO_E_CUDA, "cuTensorMapEncodeTiled(activations %llux%d) failed: %d", (unsigned long long)rows, cpitch, (int)cr2);
+    u.a_tiled = true;
+    u.a_plane_rows = (long long)max_batch * H * W;
+    u.max_batch = max_batch;
+    u.enabled = true;
+    return YOLO_OK;
+  }
   cuuint64_t gdim[4] = {(cuuint64_t)cpitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)np * max_batch};
   cuuint64_t gstr[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2};
   int lower[2] = {-u.pad, -u.pad};
@@ -693,15 +804,34 @@ void umma_release(UmmaConv& u) {
 
 static int g_num_sms = 0;
 
-template <int MODE, bool OUT_F32, bool DUAL>
+template <int MODE, bool OUT_F32, int KIND>
 static int launch_mode3(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    YB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE, OUT_F32, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    YB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE, OUT_F32, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
+  if (KIND >= 2) {
+    int pairs = g_num_sms / 2;
+    if (p.n_tiles < pairs) pairs = p.n_tiles;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    YB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<MODE, OUT_F32, KIND>, *reinterpret_cast<const CUtensorMap*>(u.map_a),
+                               *reinterpret_cast<const CUtensorMap*>(u.map_b2), p));
+    ++g_launches;
+    return YOLO_OK;
+  }
   const int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
-  conv_umma_kernel<MODE, OUT_F32, DUAL><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
+  conv_umma_kernel<MODE, OUT_F32, KIND><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
                                                                                *reinterpret_cast<const CUtensorMap*>(u.map_b), p);
   ++g_launches;
   YB_CUDA(cudaGetLastError());
@@ -710,9 +840,11 @@ static int launch_mode3(const UmmaConv& u, const UmmaParams& p, int smem_bytes, 
 template <int MODE>
 static int launch_mode(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
   if constexpr (MODE == 2) {
-    if (p.dual) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, true>(u, p, smem_bytes, st) : launch_mode3<MODE, false, true>(u, p, smem_bytes, st);
+    if (p.dual == 3) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 3>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 3>(u, p, smem_bytes, st);
+    if (p.dual == 1) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 1>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 1>(u, p, smem_bytes, st);
+    if (p.dual == 2) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 2>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 2>(u, p, smem_bytes, st);
   }
-  return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, false>(u, p, smem_bytes, st) : launch_mode3<MODE, false, false>(u, p, smem_bytes, st);
+  return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 0>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 0>(u, p, smem_bytes, st);
 }
 
 int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
@@ -736,6 +868,8 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
   p.Ho = d.Ho; p.Wo = d.Wo; p.stride = d.stride; p.pad = d.pad;
   p.in_coff = d.in_coff;
   p.a_plane_n = u.max_batch;
+  p.a_tiled = u.a_tiled ? 1 : 0;
+  p.a_plane_rows = u.a_plane_rows;
   p.b_plane_rows = p.n_tiles_n * p.BN;
   // dual-M tiles (fp16x3 only, EXPERIMENTAL, off by default; YOLO_B200_DUAL=1 enables): sharing the weight tile between two
   // M tiles cuts the TMA bytes per MMA by 25 % but measured no gain (head 3x3: 753 vs 760 us) - the main loop is bound
@@ -744,13 +878,21 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
   const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
   p.dual = 0;
   if (const char* de = getenv("YOLO_B200_DUAL")) p.dual = (de[0] == '1' && mode_of(u.precision) == 2 && m_tiles >= 2) ? 1 : 0;
+  // 2-CTA pairs (cta_group::2, 256 x BN): fp16x3, needs the half-height weight map and at least one full pair of M tiles
+  const char* pe = getenv("YOLO_B200_PAIR");
+  if (!p.dual && !u.a_tiled && mode_of(u.precision) == 2 && u.has_map_b2 && m_tiles >= 2 && p.BN % 32 == 0 && pe) {
+    if (pe[0] == '1') p.dual = 2;
+    if (pe[0] == '2' && p.n_tiles_n % 2 == 0) p.dual = 3;               // 256 x 2BN: pairs of N tiles share the activation tiles
+  }
+  if (p.dual == 3) p.n_tiles_n /= 2;                                    // scheduling units per row of the tile grid
   if (p.dual) p.n_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
-  const int stage_bytes = np * ((p.dual ? 2 : 1) * TILE_M * p.bk * 2 + p.BN * p.bk * 2);
+  const int stage_bytes = np * ((p.dual == 1 ? 2 : 1) * TILE_M * p.bk * 2 + (p.dual == 3 ? 2 : 1) * (p.dual >= 2 ? p.BN / 2 : p.BN) * p.bk * 2);
   const int aux_bytes = 16 * MAX_STAGES + 128 + 2 * 2 * p.BN * 4 + 64;
   // 8 MMAs of the leading product per TMEM partial.  Longer partials are ~3 % faster but their truncation bias is
   // systematic (same sign on every output) and compounds through the layers: flush 8 -> Darknet-53 head error 6.6e-4
   // instead of 2.9e-4 (profiles/r1_parity_report.txt).  Env YOLO_B200_FLUSH overrides for experiments.
   p.flush = p.bk == 64 ? 2 : 4;
+  if (const char* de2 = getenv("YOLO_B200_DBG_PAIRS")) p.dbg_pairs = atoi(de2);
   if (const char* fe = getenv("YOLO_B200_FLUSH")) { int f = atoi(fe); if (f >= 1 && f <= 64) p.flush = f; }
   int stages = (SMEM_LIMIT - 1024 - aux_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;

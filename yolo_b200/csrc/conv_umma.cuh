@@ -15,6 +15,10 @@ struct UmmaConv {
   size_t w_bytes = 0;
   alignas(64) unsigned char map_a[128];   // CUtensorMap (im2col) for the activations
   alignas(64) unsigned char map_b[128];   // CUtensorMap (tiled)  for the weights
+  alignas(64) unsigned char map_b2[128];  // same with a half-height box (2-CTA path)
+  bool has_map_b2 = false;
+  bool a_tiled = false;       // 1x1 conv: map_a is a tiled 2-D map over [pixels][channels]
+  long long a_plane_rows = 0;
   int max_batch = 0;
 };
 
