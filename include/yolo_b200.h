@@ -23,6 +23,8 @@
  *                                      IoU form of yolo_gluon.get_iou yolo_modules/yolo_gluon.py:158-167
  *   yolo_decode_lp                  <- YOLO.predict_LP                car_and_LP/YOLO.py:133-169 (mode 0)
  *                                      LicencePlateDetectioin.predict_LP licence_plate/LP_detection.py:147-162 (mode 1)
+ *   yolo_loss_targets               <- _loss_mask + _find_best + _score_weight + _get_loss (+ the head gradient of
+ *                                      sum(losses).backward())       car/YOLO.py:385-394,401-498, yolo_gluon.get_iou :127-168
  *   yolo_predict_host               <- cv_img_2_ndarray + net.forward + predict + asnumpy
  *                                      yolo_modules/yolo_gluon.py:335-357, car/YOLO.py:597
  */
@@ -107,6 +109,13 @@ typedef struct yolo_nms_params {
   int32_t max_cand;    /* candidates entering suppression (<= 1024)       */
 } yolo_nms_params;
 
+/* Loss hyper-parameters: spec.yaml `scale`, `positive_weight`, `negative_weight` (car/v1/spec.yaml:27-33). */
+typedef struct yolo_loss_params {
+  float   scale_score, scale_box_yx, scale_box_hw, scale_rotate, scale_class;
+  float   positive_weight, negative_weight;
+  int32_t car_rotate;   /* 0: rotate loss weight forced to 0 (car/YOLO.py:492) */
+} yolo_loss_params;
+
 const char* yolo_version(void);
 
 int  yolo_create(const yolo_spec* spec, int device, yolo_handle** out);
@@ -149,6 +158,17 @@ int  yolo_decode_nms(const yolo_decode_geom* g, const void* const* heads, int ba
  * mode 1: lp (B,ch,Hs,Ws) NCHW, argmax of the raw score, out (B,ch).  out_idx (B) may be NULL. */
 int  yolo_decode_lp(const void* lp, int batch, int hs, int ws, int ch, int mode, const float r_max[3],
                     float* out_rows, int32_t* out_idx, void* stream);
+
+/* Training targets + losses (+ head gradients), GPU-resident (no per-label host sync).
+ * labels: device fp32 (B, n_obj, 6+num_class) rows [cls, y, x, h, w, rotate, class distribution...], cls < 0 = no object.
+ * out_losses: device fp32 (5, B) = score, box_yx, box_hw, rotate, class (order of spec `loss_name`).
+ * dheads: NULL, or n_scales device fp32 tensors shaped like the heads receiving d(sum of the 5 losses)/d(head).
+ * out_assign: NULL or device int32 (B, n_obj): matched flat box index per label (-1 = no object).
+ * scratch: device memory of yolo_loss_scratch_bytes(batch, n_obj) bytes. */
+size_t yolo_loss_scratch_bytes(int batch, int n_obj);
+int  yolo_loss_targets(const yolo_decode_geom* g, const void* const* heads, const float* labels, int batch, int n_obj,
+                       const yolo_loss_params* p, void* scratch, float* out_losses, void* const* dheads, int32_t* out_assign,
+                       void* stream);
 
 /* End-to-end convenience with HOST buffers (pinned recommended): H2D, forward, decode_top1, D2H, sync.
  * CARNET / CARLPNET only.  host_rows (B, C) ; host_idx (B) may be NULL. */

@@ -1,0 +1,182 @@
+"""Oracle restatement (numpy fp32 / torch) of the reference's training targets and losses.
+
+TEST INFRASTRUCTURE ONLY - see ``oracle/__init__.py``.
+
+Follows (file:line under /root/reference):
+  * ``car/YOLO.py:209-240``   _get_default_ltrb   (anchor boxes at the cell centres, normalised ltrb)
+  * ``yolo_modules/yolo_gluon.py:127-168`` get_iou (mode 2: target = [c, y, x, h, w])
+  * ``car/YOLO.py:401-448``   _find_best          (argmax IoU -> (pixel, anchor), ty/tx/th/tw targets)
+  * ``car/YOLO.py:450-480``   _loss_mask          (dense targets; later labels overwrite earlier ones)
+  * ``car/YOLO.py:482-489``   _score_weight
+  * ``car/YOLO.py:491-498``   _get_loss           (rotate weight 0 unless car_rotate)
+and the gluon losses it instantiates at ``car/YOLO.py:185-190`` (mxnet gluon/loss.py, restated):
+  LogisticLoss(label_format='binary'): l = 2*label-1; relu(-p*l) + softrelu(-|p*l|);
+  HuberLoss(rho=1): |d| > 1 ? |d| - 0.5 : 0.5*d^2;
+  SoftmaxCrossEntropyLoss(from_logits=False, sparse_label=False): -sum(log_softmax(p) * label, -1, keepdims);
+  each multiplied by its sample weight and averaged over all non-batch axes -> (B,).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import decode
+
+f32 = np.float32
+
+
+def default_ltrb(spec, steps=None):
+    """car/YOLO.py:209-240 -> (sum(area), A, 4) fp32 [left, top, right, bottom]."""
+    steps = steps or decode.init_steps(spec)
+    area = decode.init_area(spec, steps)
+    H, W = spec["size"]
+    out = []
+    for i, anchors in enumerate(spec["all_anchors"]):
+        anchors = np.asarray(anchors, np.float32)
+        n, a, step = len(anchors), area[i], f32(steps[i])
+        h, w = anchors[:, 0], anchors[:, 1]
+        x_num, y_num = int(W / step), int(H / step)
+        # nd.arange(start, 1, step, repeat): start + i*step evaluated in fp32
+        ys = (f32(step / f32(H) / f32(2.)) + np.arange(y_num, dtype=np.float32) * f32(step / f32(H))).astype(np.float32)
+        xs = (f32(step / f32(W) / f32(2.)) + np.arange(x_num, dtype=np.float32) * f32(step / f32(W))).astype(np.float32)
+        y = np.repeat(ys, n * x_num)
+        hh = np.tile(h, a)
+        top = (y - f32(0.5) * hh).reshape(a, n, 1)
+        bot = (y + f32(0.5) * hh).reshape(a, n, 1)
+        x = np.repeat(xs, n)
+        ww = np.tile(w, x_num)
+        left = np.tile(x - f32(0.5) * ww, y_num).reshape(a, n, 1)
+        right = np.tile(x + f32(0.5) * ww, y_num).reshape(a, n, 1)
+        out.append(np.concatenate([left, top, right, bot], axis=-1).astype(np.float32))
+    return np.concatenate(out, axis=0)
+
+
+def get_iou_mode2(ltrb, L):
+    """yolo_gluon.get_iou mode 2, fp32 op by op."""
+    l, t, r, b = (ltrb[..., i] for i in range(4))
+    l2 = f32(L[2] - L[4] / f32(2)); t2 = f32(L[1] - L[3] / f32(2))
+    r2 = f32(L[2] + L[4] / f32(2)); b2 = f32(L[1] + L[3] / f32(2))
+    iw = np.maximum(np.minimum(r2, r) - np.maximum(l2, l), f32(0)).astype(np.float32)
+    ih = np.maximum(np.minimum(b2, b) - np.maximum(t2, t), f32(0)).astype(np.float32)
+    inters = (iw * ih).astype(np.float32)
+    pa = ((r - l) * (b - t)).astype(np.float32)
+    ta = f32(L[3] * L[4])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (inters / ((pa + ta).astype(np.float32) - inters)).astype(np.float32)
+
+
+def find_best(spec, ltrb, L, steps=None):
+    """car/YOLO.py:401-448 -> (flat index = pixel*A + anchor, [ty, tx, th, tw] fp32)."""
+    steps = steps or decode.init_steps(spec)
+    area = decode.init_area(spec, steps)
+    A = len(spec["all_anchors"][0])
+    H, W = spec["size"]
+    L = np.asarray(L, np.float32)
+    best = int(np.argmax(get_iou_mode2(ltrb, L).reshape(-1)))
+    px, anc = best // A, best % A
+    if px >= sum(area):
+        px = sum(area) - 1
+    bl = ltrb[px, anc]
+    a0, layer = 0, 0
+    for i, a in enumerate(area):
+        a0 += a
+        if px < a0:
+            layer = i
+            break
+    step = f32(steps[layer])
+    by = f32(L[1] - f32(f32(bl[3] + bl[1]) / f32(2)))
+    sy = np.clip(f32(f32(f32(by * f32(H)) / step) + f32(0.5)), f32(0.0001), f32(0.9999)).astype(np.float32)
+    bx = f32(L[2] - f32(f32(bl[2] + bl[0]) / f32(2)))
+    sx = np.clip(f32(f32(f32(bx * f32(W)) / step) + f32(0.5)), f32(0.0001), f32(0.9999)).astype(np.float32)
+    inv = lambda v: f32(-np.log(f32(f32(1) / v - f32(1)), dtype=np.float32))
+    anchors = np.asarray(spec["all_anchors"], np.float32)
+    th = f32(np.log(f32(L[3] / anchors[layer, anc, 0]), dtype=np.float32))
+    tw = f32(np.log(f32(L[4] / anchors[layer, anc, 1]), dtype=np.float32))
+    return px * A + anc, np.asarray([inv(sy), inv(sx), th, tw], np.float32)
+
+
+def loss_mask(spec, labels, steps=None):
+    """car/YOLO.py:450-480 -> ([score, yx, hw, rotate, class] dense targets, mask, assignment (B,obj) flat idx or -1)."""
+    labels = np.asarray(labels, np.float32)
+    B, nobj = labels.shape[:2]
+    area = decode.init_area(spec, steps)
+    a, n = sum(area), len(spec["all_anchors"][0])
+    nc = labels.shape[2] - 6
+    ltrb = default_ltrb(spec, steps)
+    mask = np.zeros((B, a, n, 1), np.float32)
+    score = np.zeros((B, a, n, 1), np.float32)
+    yx = np.zeros((B, a, n, 2), np.float32)
+    hw = np.zeros((B, a, n, 2), np.float32)
+    rot = np.zeros((B, a, n, 1), np.float32)
+    cls = np.zeros((B, a, n, nc), np.float32)
+    assign = np.full((B, nobj), -1, np.int32)
+    for b in range(B):
+        for j, L in enumerate(labels[b]):
+            if L[0] < 0:
+                continue
+            flat, box = find_best(spec, ltrb, L, steps)
+            px, anc = flat // n, flat % n
+            mask[b, px, anc] = 1.0
+            score[b, px, anc] = 1.0
+            yx[b, px, anc] = box[:2]
+            hw[b, px, anc] = box[2:]
+            rot[b, px, anc] = L[5]
+            cls[b, px, anc] = L[6:]
+            assign[b, j] = flat
+    return [score, yx, hw, rot, cls], mask, assign
+
+
+def _mean_nb(t):
+    return t.reshape(t.shape[0], -1).mean(dim=1)
+
+
+def get_loss(spec, heads, targets, mask, hp, car_rotate=False):
+    """car/YOLO.py:491-498 with the gluon loss definitions; torch fp32 so autograd gives the reference gradients.
+    heads: list of (B,HW_s,A,C) torch tensors (may require grad).  Returns the 5 losses, each (B,)."""
+    x = torch.cat(list(heads), dim=1)
+    sp = spec["slice_point"]
+    xs, i = [], 0
+    for pt in sp:
+        xs.append(x[..., i:pt]); i = pt
+    y = [torch.as_tensor(t) for t in targets]
+    m = torch.as_tensor(mask)
+    sw = torch.where(m > 0, torch.full_like(m, hp["positive_weight"]), torch.full_like(m, hp["negative_weight"]))
+
+    def logistic(p, lab, w):
+        lab = 2 * lab - 1
+        l = torch.relu(-p * lab) + torch.nn.functional.softplus(-torch.abs(p * lab))
+        return _mean_nb(l * w)
+
+    def huber(p, lab, w, rho=1.0):
+        d = torch.abs(lab - p)
+        l = torch.where(d > rho, d - 0.5 * rho, (0.5 / rho) * d * d)
+        return _mean_nb(l * w)
+
+    def softmax_ce(p, lab, w):
+        lp = torch.log_softmax(p, dim=-1)
+        l = -(lp * lab).sum(dim=-1, keepdim=True)
+        return _mean_nb(l * w)
+
+    sc = hp["scale"]
+    rot_lr = sc["rotate"] if car_rotate else 0.0
+    return (logistic(xs[0], y[0], sw * sc["score"]), huber(xs[1], y[1], m * sc["box_yx"]), huber(xs[2], y[2], m * sc["box_hw"]),
+            huber(xs[3], y[3], m * rot_lr), softmax_ce(xs[4], y[4], m * sc["class"]))
+
+
+V1_HPARAMS = dict(scale={"score": 0.1, "box_yx": 0.01, "box_hw": 10.0, "rotate": 0.0, "class": 0.3},
+                  positive_weight=1.0, negative_weight=0.1)        # car/v1/spec.yaml:27-33
+
+
+def synthetic_labels(batch, num_class, nobj=1, seed=99, p_box=0.5):
+    """with p=0.5 a box [cls, y~U(.2,.8), x~U(.2,.8), h~U(.15,.7), w~U(.15,.7), 0, soft class dist], else all -1
+    (render_car.py:80,123-132)."""
+    rng = np.random.default_rng(seed)
+    lab = np.full((batch, nobj, 6 + num_class), -1.0, np.float32)
+    for b in range(batch):
+        for j in range(nobj):
+            if rng.random() < p_box:
+                c = int(rng.integers(0, num_class))
+                d = np.exp(-((np.arange(num_class) - c) ** 2) / 2.0)
+                lab[b, j, :6] = [c, rng.uniform(.2, .8), rng.uniform(.2, .8), rng.uniform(.15, .7), rng.uniform(.15, .7), 0.0]
+                lab[b, j, 6:] = (d / d.sum()).astype(np.float32)
+    return lab

@@ -41,6 +41,11 @@ class DecodeGeom(C.Structure):
     ]
 
 
+class LossParams(C.Structure):
+    _fields_ = [("scale_score", C.c_float), ("scale_box_yx", C.c_float), ("scale_box_hw", C.c_float), ("scale_rotate", C.c_float),
+                ("scale_class", C.c_float), ("positive_weight", C.c_float), ("negative_weight", C.c_float), ("car_rotate", C.c_int32)]
+
+
 class NmsParams(C.Structure):
     _fields_ = [("score_thr", C.c_float), ("iou_thr", C.c_float), ("max_out", C.c_int32), ("max_cand", C.c_int32)]
 
@@ -65,6 +70,8 @@ SYMBOLS = {
     "yolo_decode_top1": (_I, [C.POINTER(DecodeGeom), C.POINTER(_VP), _I, _VP, _VP, _VP]),
     "yolo_decode_nms": (_I, [C.POINTER(DecodeGeom), C.POINTER(_VP), _I, C.POINTER(NmsParams), _VP, _VP, _VP, _VP]),
     "yolo_decode_lp": (_I, [_VP, _I, _I, _I, _I, _I, C.POINTER(C.c_float * 3), _VP, _VP, _VP]),
+    "yolo_loss_scratch_bytes": (_SZ, [_I, _I]),
+    "yolo_loss_targets": (_I, [C.POINTER(DecodeGeom), C.POINTER(_VP), _VP, _I, _I, C.POINTER(LossParams), _VP, _VP, C.POINTER(_VP), _VP, _VP]),
     "yolo_predict_host": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
     "yolo_last_launch_count": (_I, [_VP]),
     "yolo_conv_flops_per_image": (C.c_double, [_VP]),

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (DecodeGeom, NmsParams, YoloSpec, check, IN_NCHW_F32, IN_NHWC_U8, NET_CARNET, NET_CARLPNET,
+from ._lib import (DecodeGeom, LossParams, NmsParams, YoloSpec, check, IN_NCHW_F32, IN_NHWC_U8, NET_CARNET, NET_CARLPNET,
                    NET_LPDENSENET, NET_DEBUGCONV, PRECISIONS)
 
 NET_TYPES = {"carnet": NET_CARNET, "carlpnet": NET_CARLPNET, "lpdensenet": NET_LPDENSENET, "debugconv": NET_DEBUGCONV}
@@ -295,3 +295,31 @@ def decode_lp(lp, mode, r_max):
         check(lib.yolo_decode_lp(C.c_void_p(t.data_ptr()), B, hs, ws, ch, mode, C.byref(rm), C.c_void_p(rows.data_ptr()),
                                  C.c_void_p(idx.data_ptr()), _stream_ptr(t.device)))
     return rows, idx
+
+
+def loss_targets(spec, heads, labels, scale, positive_weight, negative_weight, car_rotate=False, with_grad=False, steps=None):
+    """Targets + losses of car/YOLO.py:385-394 (``_loss_mask`` + ``_get_loss``) on the GPU.
+
+    heads: list of (B,HW_s,A,C) cuda fp32; labels: (B,n_obj,6+num_class) cuda/np fp32.
+    Returns (losses (5,B) cuda fp32 in spec `loss_name` order, assignment (B,n_obj) cuda int32, dheads or None)."""
+    lib = _lib.load()
+    ts, ptrs = _head_ptrs(heads)
+    B, dev = ts[0].shape[0], ts[0].device
+    lab = torch.as_tensor(labels, dtype=torch.float32).to(dev).contiguous()
+    if lab.dim() != 3 or lab.shape[0] != B or lab.shape[2] != int(spec["slice_point"][-1]):
+        raise ValueError(f"labels must be (B, n_obj, 6+num_class), got {tuple(lab.shape)}")
+    n_obj = lab.shape[1]
+    g = make_geom(spec, steps)
+    p = LossParams(float(scale["score"]), float(scale["box_yx"]), float(scale["box_hw"]), float(scale["rotate"]), float(scale["class"]),
+                   float(positive_weight), float(negative_weight), int(bool(car_rotate)))
+    scratch = torch.empty(lib.yolo_loss_scratch_bytes(B, n_obj), dtype=torch.uint8, device=dev)
+    losses = torch.empty((5, B), dtype=torch.float32, device=dev)
+    assign = torch.empty((B, n_obj), dtype=torch.int32, device=dev)
+    dheads, dptrs = None, None
+    if with_grad:
+        dheads = [torch.empty_like(t) for t in ts]
+        dptrs = (C.c_void_p * len(dheads))(*[t.data_ptr() for t in dheads])
+    with torch.cuda.device(dev):
+        check(lib.yolo_loss_targets(C.byref(g), ptrs, C.c_void_p(lab.data_ptr()), B, n_obj, C.byref(p), C.c_void_p(scratch.data_ptr()),
+                                    C.c_void_p(losses.data_ptr()), dptrs, C.c_void_p(assign.data_ptr()), _stream_ptr(dev)))
+    return losses, assign, dheads

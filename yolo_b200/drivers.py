@@ -105,6 +105,16 @@ class YOLO:
         raise ValueError("mode must be 'top1' or 'nms'")
 
 
+    # -------------------- Training Part (targets + losses; backward/optimizer: next round) -------------------- #
+    def _loss_mask_and_get_loss(self, y_, car_by, car_rotate=False, with_grad=False):
+        """GPU replacement of ``_loss_mask`` + ``_score_weight`` + ``_get_loss`` (car/YOLO.py:385-392, 450-498) for one device:
+        y_ = list of head tensors from ``net.forward``, car_by = labels (b, num_object, 6+num_class).
+        Returns the five per-image losses in ``loss_name`` order as a (5, b) CUDA tensor (+ head gradients if asked)."""
+        losses, assign, dheads = api.loss_targets(self.spec, list(y_)[: len(self.steps)], car_by, self.scale, self.positive_weight,
+                                                  self.negative_weight, car_rotate, with_grad, self.steps)
+        return (losses, assign, dheads) if with_grad else (losses, assign)
+
+
 class CarLPYOLO(YOLO):
     """car_and_LP/YOLO.py ``YOLO``: CarLPNet + predict_LP."""
 
