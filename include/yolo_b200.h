@@ -25,6 +25,10 @@
  *                                      LicencePlateDetectioin.predict_LP licence_plate/LP_detection.py:147-162 (mode 1)
  *   yolo_loss_targets               <- _loss_mask + _find_best + _score_weight + _get_loss (+ the head gradient of
  *                                      sum(losses).backward())       car/YOLO.py:385-394,401-498, yolo_gluon.get_iou :127-168
+ *   yolo_train_init / yolo_train_forward_backward / yolo_train_apply
+ *                                   <- _init_train + _train_batch + gluon.Trainer.step(batch_size) with Adam
+ *                                      car/YOLO.py:157-207,350-399
+ *   yolo_get_param                  <- net.collect_params().save(...)  car/YOLO.py:546-549 (read-back for checkpoints)
  *   yolo_predict_host               <- cv_img_2_ndarray + net.forward + predict + asnumpy
  *                                      yolo_modules/yolo_gluon.py:335-357, car/YOLO.py:597
  */
@@ -169,6 +173,20 @@ size_t yolo_loss_scratch_bytes(int batch, int n_obj);
 int  yolo_loss_targets(const yolo_decode_geom* g, const void* const* heads, const float* labels, int batch, int n_obj,
                        const yolo_loss_params* p, void* scratch, float* out_losses, void* const* dheads, int32_t* out_assign,
                        void* stream);
+
+/* Training step (fp32, CARNET), one process per GPU.  The four flat buffers (parameters, gradients, Adam m, Adam v) are
+ * caller-owned device memory of yolo_train_flat_size() floats each, so the data-parallel gradient exchange is ONE
+ * all-reduce(sum) over `grads_flat` between forward_backward and apply (the reference sums over contexts inside
+ * trainer.step through kvstore 'device', car/YOLO.py:396).  BatchNorm statistics stay local to the GPU (car/YOLO.py:94-96).
+ *   forward_backward: train-mode forward, targets + the five losses -> out_losses (device, (5,B)), backward of their sum.
+ *   apply: w -= lr_t * m / (sqrt(v) + eps) with g = grads * rescale_grad (= 1/global batch), lr_t = lr*sqrt(1-b2^t)/(1-b1^t). */
+size_t yolo_train_flat_size(const yolo_handle* h);
+int  yolo_train_init(yolo_handle* h, float* params_flat, float* grads_flat, float* adam_m, float* adam_v, size_t n_flat, void* stream);
+int  yolo_train_forward_backward(yolo_handle* h, const void* input, int in_layout, const float* labels, int batch, int n_obj,
+                                 const yolo_loss_params* lp, float* out_losses, void* stream);
+int  yolo_train_apply(yolo_handle* h, float lr, float beta1, float beta2, float eps, float rescale_grad, void* stream);
+/* Read a parameter / running statistic (want_grad = 0) or its gradient (want_grad = 1) back in yolo_load_param's layout. */
+int  yolo_get_param(yolo_handle* h, const char* name, float* host, size_t n_elems, int want_grad);
 
 /* End-to-end convenience with HOST buffers (pinned recommended): H2D, forward, decode_top1, D2H, sync.
  * CARNET / CARLPNET only.  host_rows (B, C) ; host_idx (B) may be NULL. */

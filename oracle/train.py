@@ -180,3 +180,44 @@ def synthetic_labels(batch, num_class, nobj=1, seed=99, p_box=0.5):
                 lab[b, j, :6] = [c, rng.uniform(.2, .8), rng.uniform(.2, .8), rng.uniform(.15, .7), rng.uniform(.15, .7), 0.0]
                 lab[b, j, 6:] = (d / d.sum()).astype(np.float32)
     return lab
+
+
+# ---------------------------------------------------------------------------------------------------------
+# one training step (car/YOLO.py:350-399 + gluon.Trainer/Adam), torch autograd as the reference
+# ---------------------------------------------------------------------------------------------------------
+TRAINABLE = ("weight", "gamma", "beta", "bias")
+
+
+def train_step(net, spec, params, x, labels, hp, lr=0.001, batch_size=None, adam=None, t=1, car_rotate=False,
+               beta1=0.9, beta2=0.999, eps=1e-8):
+    """Forward in train mode (batch-statistics BN, per device), targets, the five losses, ``sum(losses).backward()``,
+    then ``trainer.step(batch_size)``: grad * (1/batch_size) -> MXNet ``adam_update`` with the bias-corrected lr
+    (``lr * sqrt(1-beta2^t)/(1-beta1^t)``, epsilon outside the square root, wd 0).  Single device (the multi-context sum of
+    the reference is the all-reduce of the B200 build).  Returns dict(losses, grads, params, adam)."""
+    from . import nets
+    import math
+    batch_size = batch_size or x.shape[0]
+    tp = {k: torch.tensor(np.asarray(v), dtype=torch.float32, requires_grad=k.rsplit(".", 1)[1] in TRAINABLE) for k, v in params.items()}
+    out, new_stats = nets.forward(net, spec, tp, torch.as_tensor(x), train=True)
+    heads = out if net == "carnet" else out[0]
+    targets, mask, assign = loss_mask(spec, labels)
+    losses = get_loss(spec, heads, targets, mask, hp, car_rotate)
+    sum(l.sum() for l in losses).backward()
+    grads = {k: v.grad.numpy().copy() for k, v in tp.items() if v.requires_grad}
+    adam = adam or {k: (np.zeros_like(g), np.zeros_like(g)) for k, g in grads.items()}
+    lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+    new_params, new_adam = {}, {}
+    for k, v in params.items():
+        if k in grads:
+            g = grads[k] * np.float32(1.0 / batch_size)
+            m, vv = adam[k]
+            m = (beta1 * m + (1 - beta1) * g).astype(np.float32)
+            vv = (beta2 * vv + (1 - beta2) * g * g).astype(np.float32)
+            new_params[k] = (np.asarray(v, np.float32) - np.float32(lr_t) * m / (np.sqrt(vv) + np.float32(eps))).astype(np.float32)
+            new_adam[k] = (m, vv)
+        elif k in new_stats:
+            new_params[k] = new_stats[k].detach().numpy().astype(np.float32)
+        else:
+            new_params[k] = np.asarray(v, np.float32)
+    return dict(losses=np.stack([l.detach().numpy() for l in losses]), grads=grads, params=new_params, adam=new_adam, assign=assign,
+                heads=[h.detach().numpy() for h in heads])

@@ -69,3 +69,65 @@ def test_driver_surface():
     assert losses.shape == (5, 3) and assign.shape == (3, 1)
     ol, oassign, _ = _oracle(spec, heads, labels, train.V1_HPARAMS)
     np.testing.assert_allclose(losses.cpu().numpy(), ol, rtol=2e-5, atol=1e-9)
+
+
+def _train_case(spec, B, nobj, seed):
+    C = spec["slice_point"][-1]
+    params = weights.make_params("carnet", spec, seed=seed, calib_batch=2)
+    x, _ = weights.synthetic_frames(B, spec["size"], seed=seed + 1)
+    labels = train.synthetic_labels(B, C - 6, nobj=nobj, seed=seed + 2, p_box=0.8)
+    return params, x, labels
+
+
+@pytest.mark.parametrize("spec,B", [(nets.spec_tiny(size=(64, 96), C=10), 2), (nets.spec_micro(size=(128, 128), C=8), 3)])
+def test_train_step_matches_oracle(spec, B):
+    """One full step (train-mode forward, losses, backward, Adam) against torch autograd + the restated MXNet Adam."""
+    import yolo_b200
+    params, x, labels = _train_case(spec, B, 2, 31)
+    hp = train.V1_HPARAMS
+    ref = train.train_step("carnet", spec, params, x, labels, hp, lr=0.001, batch_size=B)
+    net = yolo_b200.Net("carnet", spec, precision="fp32", max_batch=B)
+    net.load_params(params)
+    tr = yolo_b200.Trainer(net, learning_rate=0.001)
+    losses = tr.forward_backward(torch.from_numpy(x).cuda(), labels, hp["scale"], hp["positive_weight"], hp["negative_weight"])
+    np.testing.assert_allclose(losses.cpu().numpy(), ref["losses"], rtol=2e-4, atol=1e-8)
+    shapes = dict(net.param_shapes())
+    worst = 0.0
+    for name, g in ref["grads"].items():
+        got = tr.get_param(name, shapes[name], grad=True)
+        scale = max(np.abs(g).max(), 1e-6)
+        err = np.abs(got - g).max() / scale
+        worst = max(worst, err)
+        assert err < 5e-3, f"{name}: grad rel err {err:.2e} (|g|max {scale:.2e})"
+    tr.step(B)
+    # Adam's first step moves every weight by ~lr*sign(g): where |g| is comparable to epsilon (1e-8) a 1e-10 difference in
+    # the gradient changes the update, so a handful of near-zero-gradient elements may differ by up to 2*lr.
+    n_bad = n_all = 0
+    for name, v in ref["params"].items():
+        got = tr.get_param(name, shapes[name])
+        tol = 2e-5 + 2e-3 * np.abs(v).max() * name.endswith("running_var")
+        diff = np.abs(got - v)
+        assert diff.max() <= 2.1e-3 + tol, f"{name}: {diff.max():.2e}"
+        n_bad += int((diff > tol).sum()); n_all += diff.size
+    assert n_bad <= 2e-3 * n_all, f"{n_bad} of {n_all} parameters differ after the Adam step"
+    # the inference path now runs on the trained weights / refolded BN
+    heads = net.forward(data=torch.from_numpy(x).cuda())
+    tp = {k: torch.from_numpy(v) for k, v in ref["params"].items()}
+    with torch.no_grad():
+        oh = nets.forward("carnet", spec, tp, torch.from_numpy(x))
+    for a, b in zip(heads, oh):
+        np.testing.assert_allclose(a.asnumpy(), b.numpy(), rtol=0, atol=5e-4)
+
+
+def test_train_batch_driver_surface_and_loss_goes_down():
+    import yolo_b200
+    spec = dict(nets.spec_micro(size=(128, 128), C=8), classes=[0, 1], batch_size=4, learning_rate=0.001, **train.V1_HPARAMS)
+    params, x, labels = _train_case(spec, 4, 1, 7)
+    y = yolo_b200.YOLO(spec=spec, params=params, precision="fp32", max_batch=4)
+    xs = torch.from_numpy(x).cuda()
+    first = None
+    for it in range(8):
+        assert y._train_batch([xs], [labels]) is None
+        tot = float(y.last_losses.sum())
+        first = tot if first is None else first
+    assert y.backward_counter == 8 and tot < first

@@ -72,6 +72,11 @@ SYMBOLS = {
     "yolo_decode_lp": (_I, [_VP, _I, _I, _I, _I, _I, C.POINTER(C.c_float * 3), _VP, _VP, _VP]),
     "yolo_loss_scratch_bytes": (_SZ, [_I, _I]),
     "yolo_loss_targets": (_I, [C.POINTER(DecodeGeom), C.POINTER(_VP), _VP, _I, _I, C.POINTER(LossParams), _VP, _VP, C.POINTER(_VP), _VP, _VP]),
+    "yolo_train_flat_size": (_SZ, [_VP]),
+    "yolo_train_init": (_I, [_VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "yolo_train_forward_backward": (_I, [_VP, _VP, _I, _VP, _I, _I, C.POINTER(LossParams), _VP, _VP]),
+    "yolo_train_apply": (_I, [_VP, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _VP]),
+    "yolo_get_param": (_I, [_VP, C.c_char_p, _VP, _SZ, _I]),
     "yolo_predict_host": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
     "yolo_last_launch_count": (_I, [_VP]),
     "yolo_conv_flops_per_image": (C.c_double, [_VP]),

@@ -323,3 +323,54 @@ def loss_targets(spec, heads, labels, scale, positive_weight, negative_weight, c
         check(lib.yolo_loss_targets(C.byref(g), ptrs, C.c_void_p(lab.data_ptr()), B, n_obj, C.byref(p), C.c_void_p(scratch.data_ptr()),
                                     C.c_void_p(losses.data_ptr()), dptrs, C.c_void_p(assign.data_ptr()), _stream_ptr(dev)))
     return losses, assign, dheads
+
+
+class Trainer:
+    """Data-parallel training of a ``Net`` (fp32 CARNET), one process per GPU - the B200 shape of ``_init_train`` +
+    ``_train_batch`` + ``gluon.Trainer(..., 'adam').step(batch_size)`` (car/YOLO.py:157-207, 350-399).
+
+    The flat parameter / gradient / Adam buffers are torch tensors (device-memory containers); when torch.distributed is
+    initialised the gradients are summed over ranks with ONE all-reduce (NCCL over NVLink) between backward and the update,
+    mirroring the kvstore reduction inside ``trainer.step``.  BatchNorm statistics stay per GPU like in the reference."""
+
+    def __init__(self, net, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        self.net, self.lib = net, net.lib
+        self.lr, self.beta1, self.beta2, self.eps = float(learning_rate), float(beta1), float(beta2), float(epsilon)
+        n = self.lib.yolo_train_flat_size(net._h)
+        dev = net.device
+        self.P, self.G, self.M, self.V = (torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(4))
+        with torch.cuda.device(dev):
+            check(self.lib.yolo_train_init(net._h, C.c_void_p(self.P.data_ptr()), C.c_void_p(self.G.data_ptr()), C.c_void_p(self.M.data_ptr()),
+                                           C.c_void_p(self.V.data_ptr()), n, _stream_ptr(dev)), net._h)
+
+    def forward_backward(self, images, labels, scale, positive_weight, negative_weight, car_rotate=False):
+        """images: (b,3,H,W) fp32 or (b,H,W,3) uint8; labels: (b,n_obj,6+num_class).  Returns the (5,b) losses (cuda)."""
+        net = self.net
+        x = net._to_device(images).contiguous()
+        layout = IN_NCHW_F32 if x.dtype == torch.float32 else IN_NHWC_U8
+        lab = torch.as_tensor(labels, dtype=torch.float32).to(net.device).contiguous()
+        B, n_obj = x.shape[0], lab.shape[1]
+        p = LossParams(float(scale["score"]), float(scale["box_yx"]), float(scale["box_hw"]), float(scale["rotate"]), float(scale["class"]),
+                       float(positive_weight), float(negative_weight), int(bool(car_rotate)))
+        losses = torch.empty((5, B), dtype=torch.float32, device=net.device)
+        with torch.cuda.device(net.device):
+            check(self.lib.yolo_train_forward_backward(net._h, C.c_void_p(x.data_ptr()), layout, C.c_void_p(lab.data_ptr()), B, n_obj, C.byref(p),
+                                                       C.c_void_p(losses.data_ptr()), _stream_ptr(net.device)), net._h)
+        self._keep = (x, lab)
+        return losses
+
+    def allreduce_grads(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.G, op=dist.ReduceOp.SUM)
+
+    def step(self, batch_size):
+        """``trainer.step(batch_size)``: gradients (already summed over ranks) are rescaled by 1/batch_size, then Adam."""
+        with torch.cuda.device(self.net.device):
+            check(self.lib.yolo_train_apply(self.net._h, self.lr, self.beta1, self.beta2, self.eps, 1.0 / float(batch_size),
+                                            _stream_ptr(self.net.device)), self.net._h)
+
+    def get_param(self, name, shape, grad=False):
+        out = np.empty(shape, np.float32)
+        check(self.lib.yolo_get_param(self.net._h, name.encode(), out.ctypes.data_as(C.c_void_p), out.size, int(grad)), self.net._h)
+        return out

@@ -41,6 +41,7 @@ struct ConvDesc {
   const void* in;  int in_dtype;  int N, H, W, Cin;  int in_cpitch, in_coff;  long long in_plane_stride;
   // filter
   int kh, kw, stride, pad;  int Cout;
+  int in_dil;                  // >1: the input is implicitly zero-dilated (data-gradient of a strided conv); 0/1 = off
   const float* w_f32;          // [kh*kw*Cin][CoutPad4] fp32 (SIMT path), k = (r*kw+s)*Cin + c
   int cout_pad;                // row pitch of w_f32
   // prologue on the input (DenseNet pre-activation BN->ReLU): v = relu(v*pre_scale[c] + pre_shift[c])

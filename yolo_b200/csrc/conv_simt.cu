@@ -210,7 +210,12 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
       int tap = kg / d.Cin, c = kg - tap * d.Cin;
       int r = tap / d.kw, s = tap - r * d.kw;
       int ih = a_ih0 + r, iw = a_iw0 + s;
-      if (a_valid && (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W) {
+      bool ok = a_valid;
+      if (d.in_dil > 1) {                      // transposed conv: only every in_dil-th position of the dilated input is real
+        ok = ok && ih >= 0 && iw >= 0 && (ih % d.in_dil) == 0 && (iw % d.in_dil) == 0;
+        ih /= d.in_dil; iw /= d.in_dil;
+      }
+      if (ok && (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W) {
         const TIn* p = static_cast<const TIn*>(d.in) + ((size_t)(a_n * d.H + ih) * d.W + iw) * d.in_cpitch + d.in_coff + c;
         load8f<FI>(p, d.in_plane_stride, ra);
         if (d.pre_scale) {
@@ -226,7 +231,12 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
           int tap = kg / d.Cin, c = kg - tap * d.Cin;
           int r = tap / d.kw, s = tap - r * d.kw;
           int ih = a_ih0 + r, iw = a_iw0 + s;
-          if ((unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W) {
+          bool ok = true;
+          if (d.in_dil > 1) {
+            ok = ih >= 0 && iw >= 0 && (ih % d.in_dil) == 0 && (iw % d.in_dil) == 0;
+            ih /= d.in_dil; iw /= d.in_dil;
+          }
+          if (ok && (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W) {
             float v;
             if (args.in_layout == IN_NCHW_F32) {
               v = __ldg(static_cast<const float*>(d.in) + ((size_t)(a_n * d.Cin + c) * d.H + ih) * d.W + iw);

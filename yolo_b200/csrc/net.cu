@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "conv_umma.cuh"
+#include "net_internal.cuh"
 
 namespace yb {
 
@@ -43,81 +44,11 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-constexpr float kBnEps = 1e-5f;   // gluon BatchNorm() default (gluoncv _conv2d)
-
-struct Param {
-  std::string name;
-  int shape[4];
-  int ndim;
-  std::vector<float> host;
-  bool loaded = false;
-  size_t numel() const { size_t n = 1; for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i]; return n; }
-};
-
-struct Buffer {            // one activation buffer; holds max_batch images
-  size_t bytes_per_image = 0;
-  size_t offset = 0;       // byte offset inside the workspace
-  int dtype = DT_F32;
-};
-
-struct View {              // NHWC tensor or a channel slice of a wider buffer (per-image dims)
-  int buf = -1;            // >= 0 workspace buffer; -1 network input; <= -2: user output (-2 - index)
-  int H = 0, W = 0, C = 0;
-  int cpitch = 0, coff = 0;
-  int dtype = DT_F32;
-  long long ps = 0;        // plane stride in elements (DT_BF16X3: plane p lives at element offset p*ps)
-};
-
-enum OpKind { OP_CONV = 0, OP_POOL = 1 };
-
-struct Op {
-  int kind = OP_CONV;
-  std::string name;        // oracle layer name whose activation this op produces
-  View in, out, res;
-  bool has_res = false;
-  int kh = 1, kw = 1, stride = 1, pad = 0, cout = 0, act = ACT_NONE;
-  int upsample2 = 0, out_nchw = 0, is_max = 0;
-  int p_weight = -1, p_bias = -1, p_bn = -1, p_prebn = -1;   // index of the FIRST param of each group
-  // device parameter pointers (valid after finalize)
-  float* w_f32 = nullptr;
-  int cout_pad = 0;
-  float *scale = nullptr, *shift = nullptr, *pre_scale = nullptr, *pre_shift = nullptr;
-  UmmaConv umma;           // tensor-core path state (tensor maps, packed weights); engaged iff umma.enabled
-};
-
 }  // namespace yb
 
 using namespace yb;
 
-struct yolo_handle {
-  yolo_spec spec;
-  int device = 0;
-  std::string err;
-  std::vector<Param> params;
-  std::map<std::string, int> pindex;
-  std::vector<Buffer> bufs;
-  std::vector<Op> ops;
-  std::vector<View> outputs;               // per-output view (buf = -2 - i)
-  std::map<std::string, View> named;       // oracle layer name -> activation view
-  int act_dtype = DT_F32;
-  bool finalized = false;
-  void* dparams = nullptr;                 // device parameter arena
-  size_t dparams_bytes = 0;
-  char* ws = nullptr;
-  size_t ws_bytes = 0;
-  int last_launches = 0;
-  double flops_per_image = 0.0;
-  // lazily allocated device staging for yolo_predict_host
-  void* stage = nullptr;
-  size_t stage_bytes = 0;
-};
-
 namespace yb {
-
-static int hfail(yolo_handle* h, int code) {
-  if (h) h->err = tls_error();
-  return code;
-}
 
 // ------------------------------------------------------------------------------------------------
 // plan builder
@@ -431,6 +362,7 @@ extern "C" int yolo_destroy(yolo_handle* h) {
   cudaSetDevice(h->device);
   if (h->dparams) cudaFree(h->dparams);
   if (h->stage) cudaFree(h->stage);
+  train_release(h);
   for (auto& op : h->ops) umma_release(op.umma);
   delete h;
   return YOLO_OK;
@@ -718,6 +650,7 @@ extern "C" int yolo_predict_host(yolo_handle* h, const void* host_input, int bat
   const size_t o_rows = take((size_t)C * 4 * s.max_batch), o_idx = take((size_t)4 * s.max_batch);
   if (!h->stage || h->stage_bytes < total) {
     if (h->stage) cudaFree(h->stage);
+  train_release(h);
     h->stage = nullptr;
     if (cudaMalloc(&h->stage, total) != cudaSuccess) { cudaGetLastError(); return hfail(h, fail(YOLO_E_OOM, "predict_host: cudaMalloc(%zu) failed", total)); }
     h->stage_bytes = total;

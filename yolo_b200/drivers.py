@@ -115,6 +115,28 @@ class YOLO:
         return (losses, assign, dheads) if with_grad else (losses, assign)
 
 
+    def _init_train(self):
+        """car/YOLO.py:157-207: Adam(learning_rate from the spec); batch_size is the GLOBAL batch (batch_size *= len(ctx))."""
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.global_batch_size = int(getattr(self, "batch_size", self.max_batch)) * world
+        self.trainer = api.Trainer(self.net, learning_rate=getattr(self, "learning_rate", 0.001))
+        self.backward_counter = getattr(self, "train_counter_start", 0)
+
+    def _train_batch(self, bxs, car_bys, car_rotate=False):
+        """car/YOLO.py:350-399.  ``bxs`` / ``car_bys`` are lists with ONE entry (this process's GPU; the reference passes one
+        entry per context).  Side effects like the reference: parameters updated, ``backward_counter`` advanced;
+        returns None.  The per-image losses of the last step are kept in ``self.last_losses`` ((5,b), loss_name order)."""
+        if not hasattr(self, "trainer"):
+            self._init_train()
+        if len(bxs) != 1 or len(car_bys) != 1:
+            raise ValueError("one process per GPU: pass this rank's slice as single-element lists")
+        self.last_losses = self.trainer.forward_backward(bxs[0], car_bys[0], self.scale, self.positive_weight, self.negative_weight, car_rotate)
+        self.trainer.allreduce_grads()
+        self.trainer.step(self.global_batch_size)
+        self.backward_counter += 1
+
+
 class CarLPYOLO(YOLO):
     """car_and_LP/YOLO.py ``YOLO``: CarLPNet + predict_LP."""
 
