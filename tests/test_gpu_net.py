@@ -125,7 +125,8 @@ def test_dk53_416_end_to_end(precision):
     np.testing.assert_array_equal(idx, oidx)
     pred64 = decode.predict(spec, [r.astype(np.float32) for r in ref64])         # rows decoded from the fp64 heads
     assert np.abs(pred[:, :4] - opred[:, :4]).max() <= 1e-4                      # score, y, x, h vs the fp32 oracle
-    noise_aware_check(pred[:, :5], opred[:, :5], pred64[:, :5], what="dk53 score+bbox")   # w = exp(tw)*anchor > 1 amplifies
+    head_noise = max(float(np.abs(a.astype(np.float64) - b).max()) for a, b in zip(ref32, ref64))
+    noise_aware_check(pred[:, :5], opred[:, :5], pred64[:, :5], floor=max(1e-4, 4 * head_noise), what="dk53 score+bbox")   # w = exp(tw)*anchor
     sm = lambda z: np.exp(z - z.max(-1, keepdims=True)) / np.exp(z - z.max(-1, keepdims=True)).sum(-1, keepdims=True)
     np.testing.assert_allclose(sm(pred[:, 6:]), sm(opred[:, 6:]), rtol=0, atol=1e-4)   # class scores (video_node.py:246)
     # the one-call host path gives the same rows
@@ -163,7 +164,9 @@ def test_full_size_configs(name, net, spec, B, precision):
     orows, oidx = decode.predict(spec, ref32[:3], return_index=True)
     np.testing.assert_array_equal(idx.cpu().numpy(), oidx)
     rows64 = decode.predict(spec, [r.astype(np.float32) for r in ref64[:3]])
-    noise_aware_check(rows.cpu().numpy()[:, :5], orows[:, :5], rows64[:, :5], what=f"{name} score+bbox")
+    # decoded h, w = exp(t)*anchor carry the head logits' error 1:1, so the bound is the heads' noise-aware bound
+    head_noise = max(float(np.abs(a.astype(np.float64) - b).max()) for a, b in zip(ref32[:3], ref64[:3]))
+    noise_aware_check(rows.cpu().numpy()[:, :5], orows[:, :5], rows64[:, :5], floor=max(1e-4, 4 * head_noise), what=f"{name} score+bbox")
     if net == "carlpnet":
         lrows, lidx = yolo_b200.decode_lp(torch.from_numpy(res[3]).cuda(), 0, spec["LP_r_max"])
         olr, oli = decode.predict_LP_batch(spec, ref32[3], return_index=True)

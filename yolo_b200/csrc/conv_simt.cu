@@ -412,9 +412,9 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
   }
   __syncthreads();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= args.M) return;
   const int HoWo = d.Ho * d.Wo;
-  const int n = m / HoWo, rem = m - n * HoWo;
+  const int mm = m < args.M ? m : args.M - 1;
+  const int n = mm / HoWo, rem = mm - n * HoWo;
   const int oh = rem / d.Wo, ow = rem - oh * d.Wo;
   float x[27];
 #pragma unroll
@@ -433,20 +433,27 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
         x[(r * 3 + q) * 3 + c] = v;
       }
     }
+  // Results are staged in shared memory as whole pixel rows so that the block writes its 256 consecutive pixels with
+  // fully coalesced 16-byte stores (a thread-per-pixel store pattern touches 32 different lines per instruction).
+  TOut* s_out = reinterpret_cast<TOut*>(s_sh + d.Cout);          // [NP][256][Cout]
+  const bool staged = args.in_layout >= 0 && d.out_cpitch == d.Cout && d.out_coff == 0 && (d.Cout * sizeof(TOut)) % 16 == 0;
   TOut* op = static_cast<TOut*>(d.out) + (size_t)m * d.out_cpitch + d.out_coff;
+  const int m_blk0 = blockIdx.x * blockDim.x;
   for (int o0 = 0; o0 < d.Cout; o0 += STEM_CO) {
     float acc[STEM_CO];
 #pragma unroll
     for (int j = 0; j < STEM_CO; ++j) acc[j] = 0.f;
+    if (m < args.M) {
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
+      for (int k = 0; k < 27; ++k) {
 #pragma unroll
-      for (int j4 = 0; j4 < STEM_CO; j4 += 4) {
-        const float4 w = *reinterpret_cast<const float4*>(&s_w[k * cp + o0 + j4]);
-        acc[j4] = fmaf(x[k], w.x, acc[j4]);
-        acc[j4 + 1] = fmaf(x[k], w.y, acc[j4 + 1]);
-        acc[j4 + 2] = fmaf(x[k], w.z, acc[j4 + 2]);
-        acc[j4 + 3] = fmaf(x[k], w.w, acc[j4 + 3]);
+        for (int j4 = 0; j4 < STEM_CO; j4 += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(&s_w[k * cp + o0 + j4]);
+          acc[j4] = fmaf(x[k], w.x, acc[j4]);
+          acc[j4 + 1] = fmaf(x[k], w.y, acc[j4 + 1]);
+          acc[j4 + 2] = fmaf(x[k], w.z, acc[j4 + 2]);
+          acc[j4 + 3] = fmaf(x[k], w.w, acc[j4 + 3]);
+        }
       }
     }
 #pragma unroll
@@ -459,7 +466,19 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
         else if (d.act == ACT_RELU) y = fmaxf(y, 0.f);
         v[j] = y;
       }
-      store4f<FO>(op + o0 + j4, d.out_plane_stride, v);
+      if (staged) store4f<FO>(s_out + (size_t)threadIdx.x * d.Cout + o0 + j4, (long long)blockDim.x * d.Cout, v);
+      else if (m < args.M) store4f<FO>(op + o0 + j4, d.out_plane_stride, v);
+    }
+  }
+  if (staged) {
+    __syncthreads();
+    const int rows = min((int)blockDim.x, args.M - m_blk0);
+    const int vec_per_plane = rows * d.Cout * (int)sizeof(TOut) / 16;
+#pragma unroll
+    for (int q = 0; q < FO::NP; ++q) {
+      const uint4* src = reinterpret_cast<const uint4*>(s_out + (size_t)q * blockDim.x * d.Cout);
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<TOut*>(d.out) + (size_t)q * d.out_plane_stride + (size_t)m_blk0 * d.Cout);
+      for (int i = threadIdx.x; i < vec_per_plane; i += blockDim.x) dst[i] = src[i];
     }
   }
 }
@@ -467,13 +486,19 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
 template <class FO>
 static void launch_stem_t(const ConvKArgs& a, int in_layout, int smem, cudaStream_t st) {
   const int blocks = (a.M + 255) / 256;
+  static bool attr_done = false;
+  if (!attr_done) {                                        // three staged 16-bit planes need more than the default 48 KB
+    cudaFuncSetAttribute(stem3x3_kernel<FO, IN_NCHW_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(stem3x3_kernel<FO, IN_NHWC_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_done = true;
+  }
   if (in_layout == IN_NCHW_F32) stem3x3_kernel<FO, IN_NCHW_F32><<<blocks, 256, smem, st>>>(a);
   else stem3x3_kernel<FO, IN_NHWC_U8><<<blocks, 256, smem, st>>>(a);
 }
 
 bool stem_eligible(const ConvDesc& d, int in_layout) {
   return (in_layout == IN_NCHW_F32 || in_layout == IN_NHWC_U8) && d.Cin == 3 && d.kh == 3 && d.kw == 3 && d.Cout % STEM_CO == 0 &&
-         d.Cout <= 128 && !d.res && !d.pre_scale && !d.upsample2 && !d.out_nchw && ((d.out_cpitch | d.out_coff) & 7) == 0 &&
+         d.Cout <= 32 && !d.res && !d.pre_scale && !d.upsample2 && !d.out_nchw && ((d.out_cpitch | d.out_coff) & 7) == 0 &&
          d.cout_pad == d.Cout;
 }
 
@@ -483,7 +508,8 @@ int launch_stem(const ConvDesc& d, int in_layout, cudaStream_t st) {
   a.in_layout = in_layout;
   a.M = d.N * d.Ho * d.Wo;
   a.K = 27;
-  const int smem = (27 * d.cout_pad + 2 * d.Cout) * 4;
+  const int esz = d.out_dtype == DT_F32 ? 4 : 2, npl = dtype_planes(d.out_dtype);
+  const int smem = (27 * d.cout_pad + 2 * d.Cout) * 4 + npl * 256 * d.Cout * esz;      // weights, scale/shift, staged output rows
   switch (d.out_dtype) {
     case DT_F32: launch_stem_t<FmtF32>(a, in_layout, smem, st); break;
     case DT_BF16: launch_stem_t<FmtBF16>(a, in_layout, smem, st); break;

@@ -58,6 +58,7 @@ struct UmmaParams {
   int flush;                                // k-blocks per TMEM partial sum (two-level accumulation)
   int dual;                                 // 1: CTA tile = two M tiles sharing the weight tile; 2: cta_group::2 pair
   int dbg_pairs;                            // >0: issue only the first n plane pairs (timing experiments; wrong results)
+  int prefetch;                             // >0: L2-prefetch the operands of k-block kb + prefetch
   int a_tiled;                              // 1x1/s1/p0: activations are a plain [pixels][channels] matrix -> tiled TMA, not im2col
   long long a_plane_rows;                   // pixel rows per plane in that matrix (= max_batch*H*W)
   // epilogue
@@ -144,6 +145,14 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {            // ar
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// L2 prefetch of a future k-block's operand tiles (no shared memory needed): turns first-touch DRAM misses into L2 hits
+__device__ __forceinline__ void tma_prefetch_2d(const void* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_im2col_4d(const void* map, int c, int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.im2col [%0, {%1, %2, %3, %4}], {%5, %6};"
+               ::"l"(map), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const void* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -325,6 +334,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 tma2_load_2d(sb + (h * NP + pl) * b_tile_bytes, &map_b, full0, kb * p.bk, n0 + h * p.BN + pl * p.b_plane_rows);
             }
           } else {
+            if (p.prefetch > 0 && kb + p.prefetch < nkb) {
+              const int kb2 = kb + p.prefetch;
+              const int tap2 = kb2 / p.cin_blocks, cb2 = kb2 - tap2 * p.cin_blocks, r2 = tap2 / p.kw, s2 = tap2 - r2 * p.kw;
+#pragma unroll
+              for (int pl = 0; pl < NP; ++pl) {
+                if (!p.a_tiled)
+                  tma_prefetch_im2col_4d(&map_a, p.in_coff + cb2 * p.bk, bw[0], bh[0], img[0] + pl * p.a_plane_n, (uint16_t)s2, (uint16_t)r2);
+                tma_prefetch_2d(&map_b, kb2 * p.bk, n0 + pl * p.b_plane_rows);
+              }
+            }
             const uint32_t full = bar_full + 8 * stage;
             mbar_expect_tx(full, (uint32_t)stage_bytes);
 #pragma unroll
@@ -893,6 +912,7 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
   // instead of 2.9e-4 (profiles/r1_parity_report.txt).  Env YOLO_B200_FLUSH overrides for experiments.
   p.flush = p.bk == 64 ? 2 : 4;
   if (const char* de2 = getenv("YOLO_B200_DBG_PAIRS")) p.dbg_pairs = atoi(de2);
+  if (const char* pf = getenv("YOLO_B200_PREFETCH")) p.prefetch = atoi(pf);
   if (const char* fe = getenv("YOLO_B200_FLUSH")) { int f = atoi(fe); if (f >= 1 && f <= 64) p.flush = f; }
   int stages = (SMEM_LIMIT - 1024 - aux_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
