@@ -145,6 +145,16 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {            // ar
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// multicast variants (KIND 4): one TMA load lands in the shared memory of every CTA of the mask and completes on each one's barrier
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+               ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {          // cta_group::1 MMA, arrive in every CTA of the mask
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
 // L2 prefetch of a future k-block's operand tiles (no shared memory needed): turns first-touch DRAM misses into L2 hits
 __device__ __forceinline__ void tma_prefetch_2d(const void* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
@@ -232,7 +242,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // KIND 0: one 128 x BN tile per CTA.   KIND 1: two M tiles per CTA sharing the weight tile (halves along M).
   // KIND 2: CTA pair, 256 x BN.          KIND 3: CTA pair, 256 x 2BN: two N tiles sharing the activation tiles (halves along N).
   // "DUAL" = the per-half protocol: epilogue group g owns half g (its own partial/correction buffer and barriers).
-  constexpr bool DUAL = KIND == 1 || KIND == 3, PAIR = KIND == 2 || KIND == 3;
+  // KIND 4: cluster of two CTAs with ordinary 128-row MMAs whose M tiles share the weight tile: each CTA loads HALF of B and
+  //         multicasts it to both (25 % fewer TMA rows per CTA; the TMA row rate is what paces the main loop).
+  constexpr bool DUAL = KIND == 1 || KIND == 3, PAIR = KIND == 2 || KIND == 3, MCAST = KIND == 4;
+  constexpr bool CLUSTER = PAIR || MCAST;
   constexpr bool HALF_M = KIND == 1, HALF_N = KIND == 3;
   static_assert(!DUAL || MODE != 0, "dual tiles need the correction-buffer TMEM layout");
   constexpr int NMT = HALF_M ? 2 : 1;                              // A (activation) tiles per stage
@@ -259,9 +272,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   float* s_scale_all = reinterpret_cast<float*>(aux + 16 * MAX_STAGES + 128);      // [group][2][BN]: scale, shift
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
-  const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // persistent scheduling unit (CTA or CTA pair)
-  const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t cta_rank = CLUSTER ? cluster_ctarank() : 0u;
+  const int sched_id = CLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;    // persistent scheduling unit (CTA or CTA pair)
+  const int sched_n = CLUSTER ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // TMEM: two partial buffers for the leading product + two correction buffers (tile parity), each `acc_stride` columns
   const int acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : 128);
   const int tmem_cols = HAS_CORR ? 4 * acc_stride : (2 * acc_stride < 32 ? 32 : 2 * acc_stride);
@@ -273,7 +286,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     prefetch_tmap(&map_b);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, MCAST ? 2 : 1);        // MCAST: both CTAs' MMAs must have consumed the stage
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_pfull + 8 * b, 1);
@@ -293,7 +306,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   }
   tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();      // barrier inits visible to the peer before any remote arrive / TMA
+  if (CLUSTER) cluster_sync_all(); else __syncthreads();   // barrier inits visible to the peer before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -306,10 +319,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int tile = sched_id; tile < p.n_tiles; tile += sched_n) {
         const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
         const int n0 = nt * NBT * p.BN + (PAIR ? (int)cta_rank * b_rows : 0);   // HALF_N: N tile h starts at n0 + h*BN
+        const int half_rows = p.BN / 2;                                           // MCAST: weight rows this CTA fetches for both
         int img[NMT], bw[NMT], bh[NMT];
 #pragma unroll
         for (int h = 0; h < NMT; ++h) {
-          const int m0 = (PAIR ? mt * 2 + (int)cta_rank : mt * NMT + h) * TILE_M;
+          const int m0 = (CLUSTER ? mt * 2 + (int)cta_rank : mt * NMT + h) * TILE_M;
           img[h] = m0 / HoWo;
           const int rem = m0 - img[h] * HoWo;
           const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
@@ -352,12 +366,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               for (int h = 0; h < NMT; ++h) {
                 if (p.a_tiled)
                   tma_load_2d(sa + (h * NP + pl) * A_TILE_BYTES, &map_a, full, p.in_coff + cb * p.bk,
-                              (int)((mt * NMT + h) * TILE_M + pl * p.a_plane_rows));
+                              (int)((CLUSTER ? mt * 2 + (int)cta_rank : mt * NMT + h) * TILE_M + pl * p.a_plane_rows));
                 else
                   tma_load_im2col_4d(sa + (h * NP + pl) * A_TILE_BYTES, &map_a, full, p.in_coff + cb * p.bk, bw[h], bh[h],
                                      img[h] + pl * p.a_plane_n, (uint16_t)s, (uint16_t)r);
               }
-              tma_load_2d(sb + pl * b_tile_bytes, &map_b, full, kb * p.bk, n0 + pl * p.b_plane_rows);
+              if (MCAST)
+                tma_load_2d_mc(sb + pl * b_tile_bytes + (int)cta_rank * half_rows * row_bytes, &map_b, full, kb * p.bk,
+                               n0 + (int)cta_rank * half_rows + pl * p.b_plane_rows, (uint16_t)3);
+              else
+                tma_load_2d(sb + pl * b_tile_bytes, &map_b, full, kb * p.bk, n0 + pl * p.b_plane_rows);
             }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -366,7 +384,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0 && cta_rank == 0) {
+    if (lane == 0 && (cta_rank == 0 || MCAST)) {
       const uint32_t idesc = make_idesc(p.BN, MODE == 2, PAIR ? 256 : TILE_M);
       const int ksteps = p.bk / UMMA_K;
       int stage = 0;
@@ -400,6 +418,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       };
       auto commit = [&](uint32_t bar) { if (PAIR) umma2_commit_mc(bar); else umma_commit(bar); };
+      auto commit_stage = [&](uint32_t bar) { if (PAIR) umma2_commit_mc(bar); else if (MCAST) umma_commit_mc(bar, 3); else umma_commit(bar); };
       for (int tile = sched_id; tile < p.n_tiles; tile += sched_n, ++it) {
         if (!DUAL) {
           const int cbuf = it & 1;
@@ -422,7 +441,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_fence_after();
             const uint32_t sa = smem_base + stage * stage_bytes;
             issue_pairs(sa, sa + NP * A_TILE_BYTES, tmem_main, tmem_corr, main_written, corr_written);
-            commit(bar_empty + 8 * stage);                                    // frees the smem stage (in both CTAs) when the MMAs retire
+            commit_stage(bar_empty + 8 * stage);                              // frees the smem stage (in both CTAs) when the MMAs retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
             if ((kb + 1) % p.flush == 0 || kb + 1 == nkb) {                    // partial complete -> accumulation warps
               commit(bar_pfull + 8 * pbuf);
@@ -481,7 +500,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (!DUAL && group == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");
     for (int tile = sched_id + (DUAL ? 0 : group * sched_n); tile < p.n_tiles; tile += (DUAL ? 1 : 2) * sched_n, it += (DUAL ? 1 : 2)) {
       const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
-      const int m0 = (HALF_M ? mt * 2 + group : (PAIR ? mt * 2 + (int)cta_rank : mt)) * TILE_M;
+      const int m0 = (HALF_M ? mt * 2 + group : (CLUSTER ? mt * 2 + (int)cta_rank : mt)) * TILE_M;
       const int n0 = (HALF_N ? nt * 2 + group : nt) * p.BN;
       // stage scale/shift of this tile's columns (the group's previous tile is completely finished here)
       asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
@@ -655,7 +674,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 
   tc_fence_before();
-  if (PAIR) cluster_sync_all(); else __syncthreads();      // PAIR: the peer may still be arriving on / reading through this CTA
+  if (CLUSTER) cluster_sync_all(); else __syncthreads();   // the peer may still be arriving on / writing into this CTA
   if (warp == 1) {
     tc_fence_after();
     if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -723,6 +742,7 @@ int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int co
   const int np = planes_of(precision);
   u.precision = precision; u.cout = cout; u.cin = cin; u.kh = kh; u.kw = kw; u.stride = stride; u.pad = pad;
   u.bk = cin % 64 == 0 ? 64 : 32;
+  if (const char* be = getenv("YOLO_B200_BK")) { if (atoi(be) == 32) u.bk = 32; }      // experiment: more, smaller pipeline stages
   u.bn_tile = pick_bn(cout);
   const int n_tiles_n = (cout + u.bn_tile - 1) / u.bn_tile;
   const int rows = n_tiles_n * u.bn_tile;                  // zero padded so a weight tile never crosses a plane
@@ -859,6 +879,7 @@ static int launch_mode3(const UmmaConv& u, const UmmaParams& p, int smem_bytes, 
 template <int MODE>
 static int launch_mode(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
   if constexpr (MODE == 2) {
+    if (p.dual == 4) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 4>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 4>(u, p, smem_bytes, st);
     if (p.dual == 3) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 3>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 3>(u, p, smem_bytes, st);
     if (p.dual == 1) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 1>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 1>(u, p, smem_bytes, st);
     if (p.dual == 2) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 2>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 2>(u, p, smem_bytes, st);
@@ -903,9 +924,12 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
     if (pe[0] == '1') p.dual = 2;
     if (pe[0] == '2' && p.n_tiles_n % 2 == 0) p.dual = 3;               // 256 x 2BN: pairs of N tiles share the activation tiles
   }
+  // multicast clusters (KIND 4): two CTAs with neighbouring M tiles fetch half of the weight tile each and multicast it
+  const char* me = getenv("YOLO_B200_MCAST");
+  if (!p.dual && mode_of(u.precision) == 2 && u.has_map_b2 && m_tiles >= 2 && p.BN % 32 == 0 && me && me[0] == '1') p.dual = 4;
   if (p.dual == 3) p.n_tiles_n /= 2;                                    // scheduling units per row of the tile grid
   if (p.dual) p.n_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
-  const int stage_bytes = np * ((p.dual == 1 ? 2 : 1) * TILE_M * p.bk * 2 + (p.dual == 3 ? 2 : 1) * (p.dual >= 2 ? p.BN / 2 : p.BN) * p.bk * 2);
+  const int stage_bytes = np * ((p.dual == 1 ? 2 : 1) * TILE_M * p.bk * 2 + (p.dual == 3 ? 2 : 1) * ((p.dual == 2 || p.dual == 3) ? p.BN / 2 : p.BN) * p.bk * 2);
   const int aux_bytes = 16 * MAX_STAGES + 128 + 2 * 2 * p.BN * 4 + 64;
   // 8 MMAs of the leading product per TMEM partial.  Longer partials are ~3 % faster but their truncation bias is
   // systematic (same sign on every output) and compounds through the layers: flush 8 -> Darknet-53 head error 6.6e-4
