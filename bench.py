@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--size", type=int, default=416)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step probe")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -142,6 +143,42 @@ def run_reference(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(args), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def train_probe(spec, local, batch=16, steps=3):
+    """Secondary measurement (BASELINE configs[3] per-GPU batch): one data-parallel training step = train-mode forward, targets +
+    losses, backward, Adam (fp32 FFMA kernels), timed with CUDA events.  Never fails the bench: errors are reported as text."""
+    try:
+        import numpy as np
+        import torch
+
+        import yolo_b200
+        from yolo_b200 import synth
+        tspec = dict(spec, batch_size=batch, learning_rate=0.001, scale={"score": 0.1, "box_yx": 0.01, "box_hw": 10.0, "rotate": 0.0, "class": 0.3},
+                     positive_weight=1.0, negative_weight=0.1)
+        y = yolo_b200.YOLO(spec=tspec, precision="fp32", max_batch=batch, gpu=local)
+        y.net.load_params(synth.random_params(y.net.param_shapes(), seed=1, channels_per_anchor=30))
+        S = spec["size"][0]
+        x = torch.rand((batch, 3, S, S), device=f"cuda:{local}")
+        lab = np.full((batch, 1, 30), -1.0, np.float32)
+        lab[:, 0, :6] = [3, .5, .5, .3, .3, 0]
+        lab[:, 0, 6:] = 1.0 / 24
+        y._train_batch([x], [lab])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            y._train_batch([x], [lab])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out = {"images_per_s": batch / (ms / 1e3), "ms_per_step": ms, "batch_per_gpu": batch, "dtype": "f32 (FFMA kernels)",
+               "tflops": 3 * y.net.conv_flops_per_image * batch / (ms / 1e3) / 1e12, "launches_per_step": y.net.launches + 1,
+               "what": "train-mode forward + targets/losses + backward + Adam (car/YOLO.py:350-399), no all-reduce at N=1"}
+        del y
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:          # noqa: BLE001
+        return {"error": repr(e)[:300]}
 
 
 def run_ours(args):
@@ -272,6 +309,8 @@ def run_ours(args):
             "clocks": clocks, "wall_s": wall,
             "step_ms_each": [round(ev[3 * i].elapsed_time(ev[3 * i + 3]), 3) for i in range(args.steps)],
         }
+        if world == 1 and not args.no_train:
+            line["train_step"] = train_probe(spec, local)
         if world == 1 and not args.no_cpu_baseline:
             del y
             torch.cuda.empty_cache()

@@ -159,3 +159,40 @@ def test_driver_predict_surface():
     assert np.array_equal(out, decode.predict(spec, heads))
     rows, idx = y.predict(_cuda(heads), return_index=True)
     np.testing.assert_array_equal(idx, decode.predict(spec, heads, return_index=True)[1])
+
+
+def test_empty_batch_and_ragged_batch():
+    """Empty input (batch 0) is a no-op with status OK; a batch smaller than max_batch runs on the same handle."""
+    import ctypes as C
+    import yolo_b200
+    from yolo_b200 import _lib, api
+    spec = nets.spec_micro(size=(64, 96), C=10)
+    lib = _lib.load()
+    g = api.make_geom(spec)
+    heads = [torch.zeros((0, n, 3, 10), device="cuda") for n in (96, 24, 6)]
+    ptrs = (C.c_void_p * 3)(*[1, 1, 1])          # never dereferenced for batch 0
+    rows = torch.zeros((1, 10), device="cuda"); idx = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    assert lib.yolo_decode_top1(C.byref(g), ptrs, 0, C.c_void_p(rows.data_ptr()), C.c_void_p(idx.data_ptr()), None) == 0
+    assert lib.yolo_decode_lp(C.c_void_p(rows.data_ptr()), 0, 4, 4, 10, 0, C.byref((C.c_float * 3)(45, 60, 45)), C.c_void_p(rows.data_ptr()), None, None) == 0
+    r, i = yolo_b200.decode_top1(spec, [torch.from_numpy(h).cuda() for h in weights.synthetic_heads(1, spec, seed=4)])
+    assert r.shape == (1, 10) and i.shape == (1,)
+    # ragged: handle built for 4 images, called with 1 and 3
+    params = weights.make_params("carnet", spec, seed=1, calib_batch=2)
+    net = yolo_b200.Net("carnet", spec, precision="fp16x3", max_batch=4).load_params(params)
+    x, _ = weights.synthetic_frames(4, spec["size"], seed=2)
+    full = [o.asnumpy() for o in net.forward(data=torch.from_numpy(x).cuda())]
+    for b in (1, 3):
+        part = [o.asnumpy() for o in net.forward(data=torch.from_numpy(x[:b]).cuda())]
+        for a, f in zip(part, full):
+            np.testing.assert_array_equal(a, f[:b])          # per-image results do not depend on the batch
+
+
+def test_maximum_boxes_608_c80():
+    """Largest head geometry of the BASELINE configs (608x608, C=80: 22743 boxes, 7.3 MB per image): planted maximum found."""
+    spec = nets.spec_dk53((608, 608), 80)
+    heads = weights.synthetic_heads(2, spec, seed=12)
+    heads[2][1, -1, 2, 0] = 30.0
+    rows, idx = _top1(spec, heads)
+    orows, oidx = decode.predict(spec, heads, return_index=True)
+    np.testing.assert_array_equal(idx, oidx)
+    assert idx[1] == 22743 - 1 and np.array_equal(rows, orows)
