@@ -30,8 +30,8 @@ def run_layer(precision, B, H, W, cin, cout, k, stride, pad, act=LEAKY, residual
     x = rng.uniform(0, 1, size=(B, 3, H, W)).astype(np.float32)
     out = net.forward(data=torch.from_numpy(x).cuda())[0].asnumpy()           # (B, Ho, Wo, C) fp32
     pre = net.activation("pre", (B, cin, H, W))                                # exact value of the layer input
-    if residual:
-        Ho, Wo = H, W
+    if residual:                                                               # 1: + input; 2: activation-format output, no add
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
         out = net.activation("test", (B, cout, Ho, Wo)).transpose(0, 2, 3, 1)
     t = torch.from_numpy(pre).double()
     y = F.conv2d(t, torch.from_numpy(params["test.weight"]).double(), None, stride, pad)
@@ -44,7 +44,7 @@ def run_layer(precision, B, H, W, cin, cout, k, stride, pad, act=LEAKY, residual
         y = F.leaky_relu(y, 0.1)
     elif act == RELU:
         y = F.relu(y)
-    if residual:
+    if residual == 1:
         y = y + t
     return out, y.permute(0, 2, 3, 1).numpy(), net
 
@@ -63,6 +63,10 @@ SHAPES = [
     (2, 24, 24, 96, 64, 3, 2, 1, LEAKY, 0, 1),         # Cin % 64 == 32 -> 64-byte swizzle rows (BLOCK_K = 32)
     (1, 16, 16, 32, 32, 1, 1, 0, LEAKY, 1, 1),         # 1x1 residual, BLOCK_K = 32
     (1, 9, 9, 16, 24, 3, 1, 1, LEAKY, 0, 1),           # FFMA kernel in every precision
+    (2, 26, 26, 128, 256, 3, 1, 1, LEAKY, 2, 1),       # Cout % 256 == 0, 16-bit output -> 128 x 256 tiles (merged accumulation)
+    (1, 13, 13, 256, 512, 1, 1, 0, LEAKY, 2, 1),       # 1x1 on wide tiles (tiled A map), ragged M (169 pixels), two N tiles
+    (2, 16, 16, 256, 256, 3, 1, 1, LEAKY, 1, 1),       # wide tiles + residual
+    (2, 26, 26, 64, 256, 3, 2, 1, RELU, 2, 1),         # wide tiles, stride 2
 ]
 
 

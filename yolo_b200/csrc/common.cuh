@@ -27,9 +27,11 @@ extern thread_local int g_launches;
 
 enum Act : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
 // DT_BF16X3: three bf16 planes v = v0 + v1 + v2 (exact split of an fp32 value), plane p at element offset p*plane_stride
-// DT_F16X2:  two fp16 planes  v = v0 + v1 * 2^-11 (22-bit split; v1 is stored pre-scaled by 2^11 to stay normal in fp16)
+// DT_F16X2:  two fp16 planes  v = v0 + v1 (22-bit split).  v1 is stored UNSCALED so that all plane products of the tensor-core
+//            path can accumulate in one accumulator; for activations of O(1) its fp16 subnormal spacing (6e-8) is below fp32
+//            epsilon, and the weights are pre-scaled by a power of two (conv_umma.cu) so that their low plane stays normal.
 enum DType : int { DT_F32 = 0, DT_BF16 = 1, DT_BF16X3 = 2, DT_F16X2 = 3 };
-constexpr float kF16LoScale = 2048.f, kF16LoScaleInv = 1.f / 2048.f, kF16Max = 65504.f;
+constexpr float kF16LoScale = 1.f, kF16LoScaleInv = 1.f, kF16Max = 65504.f;   // low plane stored unscaled (see above)
 inline int dtype_planes(int dt) { return dt == DT_BF16X3 ? 3 : (dt == DT_F16X2 ? 2 : 1); }
 inline int dtype_bytes_per_elem(int dt) { return dt == DT_F32 ? 4 : 2 * dtype_planes(dt); }
 

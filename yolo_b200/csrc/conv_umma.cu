@@ -33,6 +33,7 @@
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <cmath>
 
 #include <vector>
 
@@ -62,6 +63,7 @@ struct UmmaParams {
   int a_tiled;                              // 1x1/s1/p0: activations are a plain [pixels][channels] matrix -> tiled TMA, not im2col
   long long a_plane_rows;                   // pixel rows per plane in that matrix (= max_batch*H*W)
   // epilogue
+  float acc_scale;                          // power of two undoing the weight pre-scale (exact)
   const float* scale;  const float* shift;  int act;
   const void* res;  int res_dtype, res_cpitch, res_coff;  long long res_plane_stride;   // elements
   void* out;  int out_dtype;  int out_cpitch, out_coff;  long long out_plane_stride;  int upsample2;
@@ -244,15 +246,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // "DUAL" = the per-half protocol: epilogue group g owns half g (its own partial/correction buffer and barriers).
   // KIND 4: cluster of two CTAs with ordinary 128-row MMAs whose M tiles share the weight tile: each CTA loads HALF of B and
   //         multicasts it to both (25 % fewer TMA rows per CTA; the TMA row rate is what paces the main loop).
-  constexpr bool DUAL = KIND == 1 || KIND == 3, PAIR = KIND == 2 || KIND == 3, MCAST = KIND == 4;
+  constexpr bool DUAL = KIND == 1 || KIND == 3, PAIR = KIND == 2 || KIND == 3 || KIND == 6, MCAST = KIND == 4;
   constexpr bool CLUSTER = PAIR || MCAST;
   constexpr bool HALF_M = KIND == 1, HALF_N = KIND == 3;
+  // KIND 5 (WIDE): one 128 x 256 tile per CTA (merged accumulation only: the two 256-column partial buffers fill the TMEM);
+  //         both accumulation groups work on every tile, group g owning columns [128 g, 128 g + 128).
+  // KIND 6: CTA pair, 256 x 256 with cta_group::2 MMAs of N = 256: each CTA stages its 128 activation rows and HALF of the 256
+  //         weight rows (64 KB per stage -> 3 stages), accumulators as in KIND 5.
+  constexpr bool WIDE = KIND == 5 || KIND == 6;
+  constexpr bool SPLIT = DUAL || WIDE;                            // both groups take part in every scheduling unit
   static_assert(!DUAL || MODE != 0, "dual tiles need the correction-buffer TMEM layout");
   constexpr int NMT = HALF_M ? 2 : 1;                              // A (activation) tiles per stage
   constexpr int NBT = HALF_N ? 2 : 1;                              // B (weight) tiles per stage
   constexpr int NP = MODE == 0 ? 1 : (MODE == 1 ? 3 : 2);          // operand planes
   constexpr int N_PAIRS = MODE == 0 ? 1 : (MODE == 1 ? 6 : 3);     // plane pairs multiplied per k-step
-  constexpr bool HAS_CORR = MODE != 0;
+  // MERGE (wide tiles, whose two 256-column partial buffers fill the TMEM): every plane pair accumulates in the partial
+  // buffer, correction products first.  The 128-column kinds keep the separate correction accumulator: measured 7 %
+  // faster there (two independent accumulation chains) at the same accuracy.
+  constexpr bool MERGE = WIDE;
+  constexpr bool HAS_CORR = MODE != 0 && !MERGE;
   const int A_TILE_BYTES = TILE_M * p.bk * 2;
   const int row_bytes = p.bk * 2;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -276,8 +288,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int sched_id = CLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;    // persistent scheduling unit (CTA or CTA pair)
   const int sched_n = CLUSTER ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // TMEM: two partial buffers for the leading product + two correction buffers (tile parity), each `acc_stride` columns
-  const int acc_stride = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : 128);
-  const int tmem_cols = HAS_CORR ? 4 * acc_stride : (2 * acc_stride < 32 ? 32 : 2 * acc_stride);
+  const int acc_stride = WIDE ? 256 : (p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : 128));
+  const int tmem_cols = WIDE ? 512 : (HAS_CORR ? 4 * acc_stride : (2 * acc_stride < 32 ? 32 : 2 * acc_stride));
   const int nkb = p.taps * p.cin_blocks;
   const int npart = (nkb + p.flush - 1) / p.flush;
 
@@ -290,7 +302,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_pfull + 8 * b, 1);
-      mbar_init(bar_pempty + 8 * b, (PAIR ? 2 : 1) * GROUP_THREADS / 32);      // PAIR: the leader collects both CTAs' groups
+      mbar_init(bar_pempty + 8 * b, (PAIR ? 2 : 1) * (WIDE ? 2 : 1) * GROUP_THREADS / 32);      // PAIR: the leader collects both CTAs' groups; WIDE: both groups drain
       mbar_init(bar_cfull + 8 * b, 1);
       mbar_init(bar_cempty + 8 * b, (PAIR ? 2 : 1) * GROUP_THREADS / 32);
     }
@@ -341,8 +353,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * (uint32_t)stage_bytes);
 #pragma unroll
             for (int pl = 0; pl < NP; ++pl) {
-              tma2_load_im2col_4d(sa + pl * A_TILE_BYTES, &map_a, full0, p.in_coff + cb * p.bk, bw[0], bh[0], img[0] + pl * p.a_plane_n,
-                                  (uint16_t)s, (uint16_t)r);
+              if (p.a_tiled)
+                tma2_load_2d(sa + pl * A_TILE_BYTES, &map_a, full0, p.in_coff + cb * p.bk, (int)((mt * 2 + (int)cta_rank) * TILE_M + pl * p.a_plane_rows));
+              else
+                tma2_load_im2col_4d(sa + pl * A_TILE_BYTES, &map_a, full0, p.in_coff + cb * p.bk, bw[0], bh[0], img[0] + pl * p.a_plane_n,
+                                    (uint16_t)s, (uint16_t)r);
 #pragma unroll
               for (int h = 0; h < NBT; ++h)
                 tma2_load_2d(sb + (h * NP + pl) * b_tile_bytes, &map_b, full0, kb * p.bk, n0 + h * p.BN + pl * p.b_plane_rows);
@@ -394,8 +409,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       auto issue_pairs = [&](uint32_t sa_tile, uint32_t sb, uint32_t tmem_main, uint32_t tmem_corr, uint32_t& main_written,
                              uint32_t& corr_written) {
 #pragma unroll
-        for (int pair = 0; pair < N_PAIRS; ++pair) {
-          if (p.dbg_pairs > 0 && pair >= p.dbg_pairs) break;
+        for (int pi = 0; pi < N_PAIRS; ++pi) {
+          // merged accumulation: the small correction products go FIRST, while the partial sum is still tiny, so that
+          // their additions do not add full-magnitude truncation steps; the leading product closes the partial
+          const int pair = MERGE ? N_PAIRS - 1 - pi : pi;
+          if (p.dbg_pairs != 0 && pair >= p.dbg_pairs) continue;          // timing experiments (-1: no MMA at all, fill + drain only)
           // pair 0 = leading product (plane 0 x plane 0) -> partial buffer; the rest -> correction accumulator
           constexpr int PA6[6] = {0, 0, 1, 0, 1, 2}, PB6[6] = {0, 1, 0, 2, 1, 0};
           constexpr int PA3[3] = {0, 0, 1}, PB3[3] = {0, 1, 0};
@@ -405,7 +423,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint64_t bdesc = make_smem_desc(sb + pb * b_tile_bytes, row_bytes);
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-            if (pair == 0) {
+            if (pair == 0 || MERGE) {
               if (PAIR) umma2_bf16(tmem_main, adesc + koff, bdesc + koff, idesc, main_written);
               else umma_bf16(tmem_main, adesc + koff, bdesc + koff, idesc, main_written);
               main_written = 1;
@@ -490,24 +508,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int lane_grp = warp & 3;                         // TMEM lane quarter this warp may access
     const int row = lane_grp * 32 + lane;                  // accumulator row = pixel within the tile
     const int HoWo = p.Ho * p.Wo;
-    float* s_scale = s_scale_all + group * 2 * p.BN;
+    const int gcols = WIDE ? 128 : p.BN;                   // accumulator columns this group owns
+    float* s_scale = s_scale_all + group * 2 * gcols;
     const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
-    const int nchunks = (p.BN + 31) >> 5;
-    int it = DUAL ? 0 : group;
+    const int nchunks = (gcols + 31) >> 5;
+    int it = SPLIT ? 0 : group;
     // Accumulation turns.  An mbarrier parity wait can only tell "this phase" from "the previous one", so a group must
     // not start waiting for its partials before the other group has consumed all of the preceding tile's partials:
     // named barriers 3/4 pass the turn (FA3-style ping-pong); group 1 donates the first turn to group 0.
-    if (!DUAL && group == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");
-    for (int tile = sched_id + (DUAL ? 0 : group * sched_n); tile < p.n_tiles; tile += (DUAL ? 1 : 2) * sched_n, it += (DUAL ? 1 : 2)) {
+    if (!SPLIT && group == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");
+    for (int tile = sched_id + (SPLIT ? 0 : group * sched_n); tile < p.n_tiles; tile += (SPLIT ? 1 : 2) * sched_n, it += (SPLIT ? 1 : 2)) {
       const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
       const int m0 = (HALF_M ? mt * 2 + group : (CLUSTER ? mt * 2 + (int)cta_rank : mt)) * TILE_M;
-      const int n0 = (HALF_N ? nt * 2 + group : nt) * p.BN;
+      const int n0 = (HALF_N ? nt * 2 + group : nt) * p.BN + (WIDE ? group * 128 : 0);
       // stage scale/shift of this tile's columns (the group's previous tile is completely finished here)
       asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
-      for (int i = et; i < p.BN; i += GROUP_THREADS) {
+      for (int i = et; i < gcols; i += GROUP_THREADS) {
         const int n = n0 + i;
         s_scale[i] = (p.scale && n < p.Cout) ? __ldg(p.scale + n) : 1.f;
-        s_scale[p.BN + i] = (p.shift && n < p.Cout) ? __ldg(p.shift + n) : 0.f;
+        s_scale[gcols + i] = (p.shift && n < p.Cout) ? __ldg(p.shift + n) : 0.f;
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
 
@@ -518,13 +537,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int i = 0; i < 32; ++i) acc[c][i] = 0.f;
 
       // ---- level 2: add the TMEM partial sums into registers (round-to-nearest) ----
-      if (!DUAL) asm volatile("bar.sync %0, 256;" ::"r"(3 + group) : "memory");           // my turn
+      if (!SPLIT) asm volatile("bar.sync %0, 256;" ::"r"(3 + group) : "memory");           // my turn
       uint32_t pc = (uint32_t)it * (uint32_t)npart;
       for (int part = 0; part < npart; ++part, ++pc) {
         const int pbuf = DUAL ? group : (int)(pc & 1);
         mbar_wait(bar_pfull + 8 * pbuf, DUAL ? (pc & 1) : ((pc >> 1) & 1));
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_addr + pbuf * acc_stride;
+        const uint32_t taddr = tmem_base + lane_addr + pbuf * acc_stride + (WIDE ? group * 128 : 0);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c < nchunks) {
@@ -560,7 +579,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_rank0(bar_cempty + 8 * cbuf)); else mbar_arrive(bar_cempty + 8 * cbuf); }
       }
 
-      if (!DUAL) asm volatile("bar.arrive %0, 256;" ::"r"(4 - group) : "memory");         // the other group's turn
+      if (!SPLIT) asm volatile("bar.arrive %0, 256;" ::"r"(4 - group) : "memory");         // the other group's turn
 
       // ---- epilogue from registers: BN affine, activation, residual, format split, store ----
       // (kept compact on purpose: the first version of this block was 17k SASS instructions and stalled on
@@ -587,7 +606,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int nvalid = min(32, p.Cout - nb);
         {
           const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
-          const float4* sh4 = reinterpret_cast<const float4*>(s_scale + p.BN + c0);
+          const float4* sh4 = reinterpret_cast<const float4*>(s_scale + gcols + c0);
           const bool leaky = p.act == ACT_LEAKY, relu = p.act == ACT_RELU;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -595,7 +614,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const float sc[4] = {a.x, a.y, a.z, a.w}, sh[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float t = fmaf(y[4 * q + e], sc[e], sh[e]);
+              float t = fmaf(y[4 * q + e] * p.acc_scale, sc[e], sh[e]);
               t = leaky ? fmaxf(t, 0.1f * t) : (relu ? fmaxf(t, 0.f) : t);
               y[4 * q + e] = t;
             }
@@ -748,11 +767,27 @@ int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int co
   const int rows = n_tiles_n * u.bn_tile;                  // zero padded so a weight tile never crosses a plane
   const size_t K = (size_t)kh * kw * cin;
   std::vector<unsigned short> host((size_t)np * rows * K, 0);
+  // fp16 planes: scale the weights by a power of two so that max|w| lands in [256, 512): the low plane (2^-12 of the
+  // value, stored unscaled) then stays a NORMAL fp16 number for all but negligible weights.  Exact; undone in the epilogue.
+  float prescale = 1.f;
+  u.acc_scale = 1.f;
+  if (precision == YOLO_PREC_FP16X3) {
+    float wmax = 0.f;
+    for (size_t i = 0; i < (size_t)cout * K; ++i) wmax = fmaxf(wmax, fabsf(w_oihw[i]));
+    if (wmax > 0.f && std::isfinite(wmax)) {
+      int e;
+      frexpf(wmax, &e);                                     // wmax = f * 2^e, f in [0.5, 1)
+      int s = 9 - e;
+      s = s < -40 ? -40 : (s > 40 ? 40 : s);
+      prescale = ldexpf(1.f, s);
+      u.acc_scale = ldexpf(1.f, -s);
+    }
+  }
   for (int o = 0; o < cout; ++o)
     for (int c = 0; c < cin; ++c)
       for (int r = 0; r < kh; ++r)
         for (int s = 0; s < kw; ++s) {
-          float v = w_oihw[(((size_t)o * cin + c) * kh + r) * kw + s];
+          float v = w_oihw[(((size_t)o * cin + c) * kh + r) * kw + s] * prescale;
           const size_t k = (size_t)(r * kw + s) * cin + c;
           if (precision == YOLO_PREC_FP16X3) {
             unsigned short h0 = f2h(v);
@@ -788,6 +823,13 @@ int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int co
     cr = g_encode_tiled(reinterpret_cast<CUtensorMap*>(u.map_b2), dt, 2, u.w_packed, gdim, gstr, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     u.has_map_b2 = cr == CUDA_SUCCESS;
+  }
+  u.has_map_bw = false;
+  if (u.bk == 64 && cout % 256 == 0 && precision != YOLO_PREC_BF16X6) {      // 256-row box for the 128 x 256 tiles
+    cuuint32_t boxw[2] = {(cuuint32_t)u.bk, 256u};
+    cr = g_encode_tiled(reinterpret_cast<CUtensorMap*>(u.map_bw), dt, 2, u.w_packed, gdim, gstr, boxw, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    u.has_map_bw = cr == CUDA_SUCCESS;
   }
   u.eligible = true;
   return YOLO_OK;
@@ -850,7 +892,7 @@ static int launch_mode3(const UmmaConv& u, const UmmaParams& p, int smem_bytes, 
     YB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MODE, OUT_F32, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
-  if (KIND >= 2) {
+  if ((KIND >= 2 && KIND <= 4) || KIND == 6) {
     int pairs = g_num_sms / 2;
     if (p.n_tiles < pairs) pairs = p.n_tiles;
     cudaLaunchConfig_t cfg;
@@ -865,19 +907,23 @@ static int launch_mode3(const UmmaConv& u, const UmmaParams& p, int smem_bytes, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     YB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<MODE, OUT_F32, KIND>, *reinterpret_cast<const CUtensorMap*>(u.map_a),
-                               *reinterpret_cast<const CUtensorMap*>(u.map_b2), p));
+                               *reinterpret_cast<const CUtensorMap*>(KIND == 6 ? u.map_b : u.map_b2), p));
     ++g_launches;
     return YOLO_OK;
   }
   const int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
   conv_umma_kernel<MODE, OUT_F32, KIND><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
-                                                                               *reinterpret_cast<const CUtensorMap*>(u.map_b), p);
+                                                                               *reinterpret_cast<const CUtensorMap*>(KIND == 5 ? u.map_bw : u.map_b), p);
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
 }
 template <int MODE>
 static int launch_mode(const UmmaConv& u, const UmmaParams& p, int smem_bytes, cudaStream_t st) {
+  if constexpr (MODE != 1) {
+    if (p.dual == 5 && p.out_dtype != DT_F32) return launch_mode3<MODE, false, 5>(u, p, smem_bytes, st);
+    if (p.dual == 6 && p.out_dtype != DT_F32) return launch_mode3<MODE, false, 6>(u, p, smem_bytes, st);
+  }
   if constexpr (MODE == 2) {
     if (p.dual == 4) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 4>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 4>(u, p, smem_bytes, st);
     if (p.dual == 3) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 3>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 3>(u, p, smem_bytes, st);
@@ -927,14 +973,30 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
   // multicast clusters (KIND 4): two CTAs with neighbouring M tiles fetch half of the weight tile each and multicast it
   const char* me = getenv("YOLO_B200_MCAST");
   if (!p.dual && mode_of(u.precision) == 2 && u.has_map_b2 && m_tiles >= 2 && p.BN % 32 == 0 && me && me[0] == '1') p.dual = 4;
+  // wide tiles (KIND 5): 128 x 256, merged accumulation
+  // (default where Cout % 256 == 0: shared-memory bytes per flop drop by 25 % - the main loop is bound by the shared-memory
+  //  port, MMA operand reads + TMA fill - measured 1.36x on the Darknet-53 step; YOLO_B200_WIDE=0 switches it off)
+  const char* we = getenv("YOLO_B200_WIDE");
+  if (!p.dual && u.has_map_bw && d.out_dtype != DT_F32 && !(we && we[0] == '0')) {
+    p.dual = 5;
+    p.BN = 256;
+    p.n_tiles_n = d.Cout / 256;
+    p.n_tiles = m_tiles * p.n_tiles_n;
+  }
+  // wide pairs (KIND 6): 256 x 256 per CTA pair (EXPERIMENT: YOLO_B200_PAIRWIDE=1)
+  const char* pw = getenv("YOLO_B200_PAIRWIDE");
+  if (p.dual == 5 && m_tiles >= 2 && u.bn_tile == 128 && pw && pw[0] == '1') p.dual = 6;
   if (p.dual == 3) p.n_tiles_n /= 2;                                    // scheduling units per row of the tile grid
-  if (p.dual) p.n_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
-  const int stage_bytes = np * ((p.dual == 1 ? 2 : 1) * TILE_M * p.bk * 2 + (p.dual == 3 ? 2 : 1) * ((p.dual == 2 || p.dual == 3) ? p.BN / 2 : p.BN) * p.bk * 2);
+  if (p.dual && p.dual != 5) p.n_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
+  const int stage_bytes = np * ((p.dual == 1 ? 2 : 1) * TILE_M * p.bk * 2 + (p.dual == 3 ? 2 : 1) * ((p.dual == 2 || p.dual == 3 || p.dual == 6) ? p.BN / 2 : p.BN) * p.bk * 2);
   const int aux_bytes = 16 * MAX_STAGES + 128 + 2 * 2 * p.BN * 4 + 64;
   // 8 MMAs of the leading product per TMEM partial.  Longer partials are ~3 % faster but their truncation bias is
   // systematic (same sign on every output) and compounds through the layers: flush 8 -> Darknet-53 head error 6.6e-4
   // instead of 2.9e-4 (profiles/r1_parity_report.txt).  Env YOLO_B200_FLUSH overrides for experiments.
   p.flush = p.bk == 64 ? 2 : 4;
+  // merged accumulation (default): every plane pair accumulates in the partial buffer, correction products first, one
+  // k-block per partial.  Measured better AND faster than the separate correction accumulator (r1_ncu_summary.md).
+  if (p.dual == 5 || p.dual == 6) p.flush = 1;                                          // merged accumulation: one k-block (12 MMAs) per partial
   if (const char* de2 = getenv("YOLO_B200_DBG_PAIRS")) p.dbg_pairs = atoi(de2);
   if (const char* pf = getenv("YOLO_B200_PREFETCH")) p.prefetch = atoi(pf);
   if (const char* fe = getenv("YOLO_B200_FLUSH")) { int f = atoi(fe); if (f >= 1 && f <= 64) p.flush = f; }
@@ -942,6 +1004,7 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return fail(YOLO_E_UNSUPPORTED, "umma: tile does not fit two pipeline stages");
   p.stages = stages;
+  p.acc_scale = u.acc_scale;
   p.scale = d.scale; p.shift = d.shift; p.act = d.act;
   p.res = d.res; p.res_dtype = d.out_dtype; p.res_cpitch = d.res_cpitch; p.res_coff = d.res_coff;
   p.out = d.out; p.out_dtype = d.out_dtype; p.out_cpitch = d.out_cpitch; p.out_coff = d.out_coff; p.upsample2 = d.upsample2;

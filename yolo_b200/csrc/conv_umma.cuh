@@ -17,9 +17,12 @@ struct UmmaConv {
   alignas(64) unsigned char map_b[128];   // CUtensorMap (tiled)  for the weights
   alignas(64) unsigned char map_b2[128];  // same with a half-height box (2-CTA path)
   bool has_map_b2 = false;
+  alignas(64) unsigned char map_bw[128];  // same with a 256-row box (128 x 256 tiles)
+  bool has_map_bw = false;
   bool a_tiled = false;       // 1x1 conv: map_a is a tiled 2-D map over [pixels][channels]
   long long a_plane_rows = 0;
   int max_batch = 0;
+  float acc_scale = 1.f;     // 2^-s: the packed weights are pre-scaled by 2^s (fp16 planes stay normal), undone in the epilogue
 };
 
 int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int cout, int cin, int kh, int kw, int stride,

@@ -230,7 +230,9 @@ struct Builder {
     const yolo_spec& s = h->spec;
     const int cin = s.channels[0], cout = s.channels[1], k = s.layers[0], stride = s.layers[1], pad = s.layers[2];
     const int act = s.layers[3], residual = s.layers[4], bn = s.layers[5];
-    if (cin < 1 || cout < 1 || k < 1 || stride < 1 || pad < 0 || (residual && (cin != cout || stride != 1 || 2 * pad != k - 1)))
+    // residual: 0 = fp32 output; 1 = + input, stored in the activation format; 2 = activation format without the add
+    if (cin < 1 || cout < 1 || k < 1 || stride < 1 || pad < 0 || residual < 0 || residual > 2 ||
+        (residual == 1 && (cin != cout || stride != 1 || 2 * pad != k - 1)))
       return fail(YOLO_E_BADARG, "spec: debug conv parameters invalid");
     View in;
     in.buf = -1; in.H = s.height; in.W = s.width; in.C = 3; in.cpitch = 3; in.coff = 0; in.dtype = DT_F32;
@@ -241,7 +243,7 @@ struct Builder {
     if (residual) {
       // residual adds need matching storage formats: route through an activation buffer, then a 1x1 "copy" is not
       // exact - instead keep the residual conv in activation format and expose it by name ("test")
-      conv("test", "test", x, cout, k, pad, stride, act, bn ? "test" : "", bn ? "" : "test", "", nullptr, &x);
+      conv("test", "test", x, cout, k, pad, stride, act, bn ? "test" : "", bn ? "" : "test", "", nullptr, residual == 1 ? &x : nullptr);
       View y = h->named["test"];
       // fp32 view of the result for the caller: identity 1x1 conv would round; the test reads "test" by name instead.
       conv("out", "out", y, 8, 1, 0, 1, ACT_NONE, "", "out", "", &o);
