@@ -63,7 +63,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
 
     def start(self):
         try:
@@ -78,6 +78,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self, wait_s=3.0):
+        """Call right before the timed region: waits until nvidia-smi delivers (its start-up takes driver locks that
+        can stall a kernel submission for tens of ms - keep that out of the timed steps) and drops the earlier samples."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < wait_s:
+            time.sleep(0.02)
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -88,7 +96,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        for ln in (self.lines[self.first:] or self.lines[-1:]):      # very short runs: fall back to the latest sample
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -222,13 +230,15 @@ def run_ours(args):
         return out, rows, idx
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         step_resident()
     launches_per_step = y.net.launches + 1
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     barrier()
     t_wall0 = time.perf_counter()

@@ -49,6 +49,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct UmmaParams {
   int M, Cout, BN, n_tiles_n, n_tiles;
+  int mt_begin;                             // first M tile of this launch (a layer may be split into a wide and a narrow launch)
   int taps, kw, cin_blocks;                 // k-blocks = taps * cin_blocks
   int bk;                                   // K elements per pipeline stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows)
   int Ho, Wo, stride, pad;
@@ -329,7 +330,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t phase = 0;
       const int HoWo = p.Ho * p.Wo;
       for (int tile = sched_id; tile < p.n_tiles; tile += sched_n) {
-        const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
+        const int mt0 = tile / p.n_tiles_n, nt = tile - mt0 * p.n_tiles_n, mt = mt0 + p.mt_begin;
         const int n0 = nt * NBT * p.BN + (PAIR ? (int)cta_rank * b_rows : 0);   // HALF_N: N tile h starts at n0 + h*BN
         const int half_rows = p.BN / 2;                                           // MCAST: weight rows this CTA fetches for both
         int img[NMT], bw[NMT], bh[NMT];
@@ -518,7 +519,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // named barriers 3/4 pass the turn (FA3-style ping-pong); group 1 donates the first turn to group 0.
     if (!SPLIT && group == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");
     for (int tile = sched_id + (SPLIT ? 0 : group * sched_n); tile < p.n_tiles; tile += (SPLIT ? 1 : 2) * sched_n, it += (SPLIT ? 1 : 2)) {
-      const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
+      const int mt0 = tile / p.n_tiles_n, nt = tile - mt0 * p.n_tiles_n, mt = mt0 + p.mt_begin;
       const int m0 = (HALF_M ? mt * 2 + group : (CLUSTER ? mt * 2 + (int)cta_rank : mt)) * TILE_M;
       const int n0 = (HALF_N ? nt * 2 + group : nt) * p.BN + (WIDE ? group * 128 : 0);
       // stage scale/shift of this tile's columns (the group's previous tile is completely finished here)
@@ -933,7 +934,8 @@ static int launch_mode(const UmmaConv& u, const UmmaParams& p, int smem_bytes, c
   return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 0>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 0>(u, p, smem_bytes, st);
 }
 
-int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
+// One launch over the M tiles [mt_begin, mt_begin + mt_count) of the layer (mt_count <= 0: all of them).
+static int launch_range(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, int mt_begin, int mt_count, bool allow_wide) {
   if (!u.enabled) return fail(YOLO_E_STATE, "umma: tensor maps not built");
   if (d.N > u.max_batch) return fail(YOLO_E_SHAPE, "umma: batch %d exceeds the tensor map's %d", d.N, u.max_batch);
   if (g_num_sms == 0) {
@@ -961,7 +963,9 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
   // M tiles cuts the TMA bytes per MMA by 25 % but measured no gain (head 3x3: 753 vs 760 us) - the main loop is bound
   // by SHARED-MEMORY bandwidth (MMA operand reads + TMA fill = 213 B/clk at 128x128 vs the 128 B/clk port), which this
   // does not change enough; see profiles/r1_ncu_summary.md.  The real fix is cta_group::2 with 256x256 tiles.
-  const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
+  const int m_tiles = mt_count > 0 ? mt_count : (p.M + TILE_M - 1) / TILE_M;
+  p.mt_begin = mt_begin;
+  p.n_tiles = m_tiles * p.n_tiles_n;
   p.dual = 0;
   if (const char* de = getenv("YOLO_B200_DUAL")) p.dual = (de[0] == '1' && mode_of(u.precision) == 2 && m_tiles >= 2) ? 1 : 0;
   // 2-CTA pairs (cta_group::2, 256 x BN): fp16x3, needs the half-height weight map and at least one full pair of M tiles
@@ -977,7 +981,7 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
   // (default where Cout % 256 == 0: shared-memory bytes per flop drop by 25 % - the main loop is bound by the shared-memory
   //  port, MMA operand reads + TMA fill - measured 1.36x on the Darknet-53 step; YOLO_B200_WIDE=0 switches it off)
   const char* we = getenv("YOLO_B200_WIDE");
-  if (!p.dual && u.has_map_bw && d.out_dtype != DT_F32 && !(we && we[0] == '0')) {
+  if (!p.dual && allow_wide && u.has_map_bw && d.out_dtype != DT_F32 && !(we && we[0] == '0')) {
     p.dual = 5;
     p.BN = 256;
     p.n_tiles_n = d.Cout / 256;
@@ -1019,6 +1023,42 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
     case 1: return launch_mode<1>(u, p, smem_bytes, st);
     default: return launch_mode<2>(u, p, smem_bytes, st);
   }
+}
+
+// Wave quantisation (EXPERIMENT, YOLO_B200_SPLIT=1; off by default).  A persistent launch runs ceil(tiles / SMs) rounds of
+// tiles, and with 128 x 256 tiles the layers of the 13^2 and 26^2 maps have only 1.2 - 4.6 rounds: the last, partly filled
+// round costs as much as a full one.  A layer can be split along M: as many FULL rounds of wide tiles as fit, and the remaining
+// M tiles as 128 x 128 tiles in a second launch.  Measured: a narrow tile costs 0.75-0.85 of a wide one (not 0.5), and the
+// second launch ~10 us, so the step got 3 % SLOWER with the split (15.45 vs 14.94 ms); the planner is kept for the record.
+int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
+  const char* we = getenv("YOLO_B200_WIDE");
+  const char* se = getenv("YOLO_B200_SPLIT");
+  const bool wide_ok = u.enabled && u.has_map_bw && d.out_dtype != DT_F32 && !(we && we[0] == '0') && !getenv("YOLO_B200_DUAL") &&
+                       !getenv("YOLO_B200_PAIR") && !getenv("YOLO_B200_MCAST") && !getenv("YOLO_B200_PAIRWIDE");
+  if (!wide_ok || !(se && se[0] == '1')) return launch_range(u, d, st, 0, 0, true);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    YB_CUDA(cudaGetDevice(&dev));
+    YB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int m_tiles = (d.N * d.Ho * d.Wo + TILE_M - 1) / TILE_M;
+  const int n_w = d.Cout / 256, n_n = 2 * n_w, sms = g_num_sms;
+  const double c_n = 0.78;                                            // narrow tile time / wide tile time (measured, head 3x3 layers)
+  const double second_launch = 10.0 / (1.6 * d.kh * d.kw * (d.Cin / 64)); // ~10 us of launch + prologue + tail, in wide-tile times
+  auto rounds = [&](int tiles) { return (tiles + sms - 1) / sms; };
+  int best_mw = m_tiles;
+  double best = rounds(m_tiles * n_w) * 1.0;
+  for (int w = 0; w <= rounds(m_tiles * n_w); ++w) {
+    int mw = (int)(((long long)w * sms) / n_w);
+    if (mw > m_tiles) mw = m_tiles;
+    const double cost = rounds(mw * n_w) * 1.0 + rounds((m_tiles - mw) * n_n) * c_n + ((mw > 0 && mw < m_tiles) ? second_launch : 0.0);
+    if (cost < best - 1e-9) { best = cost; best_mw = mw; }
+  }
+  if (best_mw == m_tiles) return launch_range(u, d, st, 0, 0, true);
+  if (best_mw == 0) return launch_range(u, d, st, 0, 0, false);
+  int rc = launch_range(u, d, st, 0, best_mw, true);
+  if (rc) return rc;
+  return launch_range(u, d, st, best_mw, m_tiles - best_mw, false);
 }
 
 }  // namespace yb
