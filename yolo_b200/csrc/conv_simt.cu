@@ -439,6 +439,10 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
   const bool staged = args.in_layout >= 0 && d.out_cpitch == d.Cout && d.out_coff == 0 && (d.Cout * sizeof(TOut)) % 16 == 0;
   TOut* op = static_cast<TOut*>(d.out) + (size_t)m * d.out_cpitch + d.out_coff;
   const int m_blk0 = blockIdx.x * blockDim.x;
+  constexpr int SW_E = 16 / (int)sizeof(TOut);                     // elements per 16-byte vector
+  const int sw_vpp = d.Cout / SW_E;                                // vectors per pixel row (power of two: Cout is 16 or 32)
+  const int sw_rpl = max(1, 128 / (d.Cout * (int)sizeof(TOut)));   // pixel rows per 128-byte bank line
+  const int sw_x = ((int)threadIdx.x / sw_rpl) & (sw_vpp - 1);
   for (int o0 = 0; o0 < d.Cout; o0 += STEM_CO) {
     float acc[STEM_CO];
 #pragma unroll
@@ -466,8 +470,12 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
         else if (d.act == ACT_RELU) y = fmaxf(y, 0.f);
         v[j] = y;
       }
-      if (staged) store4f<FO>(s_out + (size_t)threadIdx.x * d.Cout + o0 + j4, (long long)blockDim.x * d.Cout, v);
-      else if (m < args.M) store4f<FO>(op + o0 + j4, d.out_plane_stride, v);
+      if (staged) {
+        // 16-byte vectors of a pixel row are XOR-swizzled with the pixel index: a plain [pixel][Cout] staging buffer puts the
+        // 32 threads of a store on 2-4 banks (row pitch 64/128 bytes), 16-way conflicts; un-swizzled again by the copy-out
+        const int e = o0 + j4, vi = e / SW_E, within = e - vi * SW_E;
+        store4f<FO>(s_out + (size_t)threadIdx.x * d.Cout + ((vi ^ sw_x) * SW_E) + within, (long long)blockDim.x * d.Cout, v);
+      } else if (m < args.M) store4f<FO>(op + o0 + j4, d.out_plane_stride, v);
     }
   }
   if (staged) {
@@ -478,7 +486,10 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
     for (int q = 0; q < FO::NP; ++q) {
       const uint4* src = reinterpret_cast<const uint4*>(s_out + (size_t)q * blockDim.x * d.Cout);
       uint4* dst = reinterpret_cast<uint4*>(static_cast<TOut*>(d.out) + (size_t)q * d.out_plane_stride + (size_t)m_blk0 * d.Cout);
-      for (int i = threadIdx.x; i < vec_per_plane; i += blockDim.x) dst[i] = src[i];
+      for (int i = threadIdx.x; i < vec_per_plane; i += blockDim.x) {
+        const int pix = i / sw_vpp, vi = i - pix * sw_vpp;
+        dst[i] = src[pix * sw_vpp + (vi ^ ((pix / sw_rpl) & (sw_vpp - 1)))];
+      }
     }
   }
 }
