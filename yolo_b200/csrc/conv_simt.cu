@@ -436,7 +436,8 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
   // Results are staged in shared memory as whole pixel rows so that the block writes its 256 consecutive pixels with
   // fully coalesced 16-byte stores (a thread-per-pixel store pattern touches 32 different lines per instruction).
   TOut* s_out = reinterpret_cast<TOut*>(s_sh + d.Cout);          // [NP][256][Cout]
-  const bool staged = args.in_layout >= 0 && d.out_cpitch == d.Cout && d.out_coff == 0 && (d.Cout * sizeof(TOut)) % 16 == 0;
+  const bool staged = args.in_layout >= 0 && (d.Cout * sizeof(TOut)) % 16 == 0 && (d.out_cpitch * sizeof(TOut)) % 16 == 0 &&
+                      (d.out_coff * sizeof(TOut)) % 16 == 0 && (d.out_plane_stride * sizeof(TOut)) % 16 == 0;
   TOut* op = static_cast<TOut*>(d.out) + (size_t)m * d.out_cpitch + d.out_coff;
   const int m_blk0 = blockIdx.x * blockDim.x;
   constexpr int SW_E = 16 / (int)sizeof(TOut);                     // elements per 16-byte vector
@@ -485,10 +486,10 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
 #pragma unroll
     for (int q = 0; q < FO::NP; ++q) {
       const uint4* src = reinterpret_cast<const uint4*>(s_out + (size_t)q * blockDim.x * d.Cout);
-      uint4* dst = reinterpret_cast<uint4*>(static_cast<TOut*>(d.out) + (size_t)q * d.out_plane_stride + (size_t)m_blk0 * d.Cout);
+      TOut* dst = static_cast<TOut*>(d.out) + (size_t)q * d.out_plane_stride + (size_t)m_blk0 * d.out_cpitch + d.out_coff;
       for (int i = threadIdx.x; i < vec_per_plane; i += blockDim.x) {
         const int pix = i / sw_vpp, vi = i - pix * sw_vpp;
-        dst[i] = src[pix * sw_vpp + (vi ^ ((pix / sw_rpl) & (sw_vpp - 1)))];
+        *reinterpret_cast<uint4*>(dst + (size_t)pix * d.out_cpitch + vi * SW_E) = src[pix * sw_vpp + (vi ^ ((pix / sw_rpl) & (sw_vpp - 1)))];
       }
     }
   }

@@ -255,11 +255,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // KIND 6: CTA pair, 256 x 256 with cta_group::2 MMAs of N = 256: each CTA stages its 128 activation rows and HALF of the 256
   //         weight rows (64 KB per stage -> 3 stages), accumulators as in KIND 5.
   constexpr bool WIDE = KIND == 5 || KIND == 6;
+  // KIND 7 (C32I): Cin = 32 with PLANE-INTERLEAVED activations (pixel row = [hi(32) | lo(32)] = one 128-byte row instead of two
+  //         64-byte rows, which cost twice as much per byte to land).  One k-block = one filter tap, K' = 64: weight plane X =
+  //         [w_hi | w_hi] gives hi*hi (k-steps 0,1 -> partial) and lo*hi (k-steps 2,3 -> correction), plane Y = [w_lo | 0]
+  //         gives hi*lo (k-steps 0,1 -> correction).  Same six MMAs per tap as the planar layout.
+  constexpr bool C32I = KIND == 7;
+  static_assert(!C32I || MODE == 2, "interleaved planes exist for the fp16 split only");
   constexpr bool SPLIT = DUAL || WIDE;                            // both groups take part in every scheduling unit
   static_assert(!DUAL || MODE != 0, "dual tiles need the correction-buffer TMEM layout");
   constexpr int NMT = HALF_M ? 2 : 1;                              // A (activation) tiles per stage
   constexpr int NBT = HALF_N ? 2 : 1;                              // B (weight) tiles per stage
   constexpr int NP = MODE == 0 ? 1 : (MODE == 1 ? 3 : 2);          // operand planes
+  constexpr int NPA = C32I ? 1 : NP;                               // activation tiles per stage and M tile
   constexpr int N_PAIRS = MODE == 0 ? 1 : (MODE == 1 ? 6 : 3);     // plane pairs multiplied per k-step
   // MERGE (wide tiles, whose two 256-column partial buffers fill the TMEM): every plane pair accumulates in the partial
   // buffer, correction products first.  The 128-column kinds keep the separate correction accumulator: measured 7 %
@@ -274,7 +281,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int b_rows = PAIR ? p.BN / 2 : p.BN;                        // weight rows staged by this CTA
   const int b_tile_bytes = b_rows * p.bk * 2;
-  const int stage_bytes = NP * (NMT * A_TILE_BYTES + NBT * b_tile_bytes);
+  const int stage_bytes = NPA * NMT * A_TILE_BYTES + NP * NBT * b_tile_bytes;
   const uint32_t tiles_end = smem_base + p.stages * stage_bytes;
   unsigned char* aux = smem_gen + (size_t)p.stages * stage_bytes;
   // barrier layout (8 bytes each): full[8] empty[8] pfull[2] pempty[2] cfull[2] cempty[2]
@@ -347,7 +354,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int r = tap / p.kw, s = tap - r * p.kw;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + NMT * NP * A_TILE_BYTES;
+          const uint32_t sb = sa + NMT * NPA * A_TILE_BYTES;
           if (PAIR) {
             // both CTAs' bytes complete on the LEADER's full barrier, which the leader arms for 2 x stage_bytes
             const uint32_t full0 = mapa_rank0(bar_full + 8 * stage);
@@ -380,6 +387,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int pl = 0; pl < NP; ++pl) {
 #pragma unroll
               for (int h = 0; h < NMT; ++h) {
+                if (pl >= NPA) break;
                 if (p.a_tiled)
                   tma_load_2d(sa + (h * NP + pl) * A_TILE_BYTES, &map_a, full, p.in_coff + cb * p.bk,
                               (int)((CLUSTER ? mt * 2 + (int)cta_rank : mt * NMT + h) * TILE_M + pl * p.a_plane_rows));
@@ -409,6 +417,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t pcount = 0;                                                     // partial buffers handed out so far
       auto issue_pairs = [&](uint32_t sa_tile, uint32_t sb, uint32_t tmem_main, uint32_t tmem_corr, uint32_t& main_written,
                              uint32_t& corr_written) {
+        if constexpr (C32I) {
+          const uint64_t adesc = make_smem_desc(sa_tile, row_bytes);
+          const uint64_t bx = make_smem_desc(sb, row_bytes), by = make_smem_desc(sb + b_tile_bytes, row_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                                      // [hi | lo] x [w_hi | w_hi]
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+            if (k < 2) { umma_bf16(tmem_main, adesc + koff, bx + koff, idesc, main_written); main_written = 1; }
+            else if (p.dbg_pairs == 0 || p.dbg_pairs > 1) { umma_bf16(tmem_corr, adesc + koff, bx + koff, idesc, corr_written); corr_written = 1; }
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {                                      // hi x w_lo
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+            if (p.dbg_pairs == 0 || p.dbg_pairs > 2) { umma_bf16(tmem_corr, adesc + koff, by + koff, idesc, corr_written); corr_written = 1; }
+          }
+        } else {
 #pragma unroll
         for (int pi = 0; pi < N_PAIRS; ++pi) {
           // merged accumulation: the small correction products go FIRST, while the partial sum is still tiny, so that
@@ -435,6 +458,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           }
         }
+        }
       };
       auto commit = [&](uint32_t bar) { if (PAIR) umma2_commit_mc(bar); else umma_commit(bar); };
       auto commit_stage = [&](uint32_t bar) { if (PAIR) umma2_commit_mc(bar); else if (MCAST) umma_commit_mc(bar, 3); else umma_commit(bar); };
@@ -459,7 +483,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
             const uint32_t sa = smem_base + stage * stage_bytes;
-            issue_pairs(sa, sa + NP * A_TILE_BYTES, tmem_main, tmem_corr, main_written, corr_written);
+            issue_pairs(sa, sa + NPA * A_TILE_BYTES, tmem_main, tmem_corr, main_written, corr_written);
             commit_stage(bar_empty + 8 * stage);                              // frees the smem stage (in both CTAs) when the MMAs retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
             if ((kb + 1) % p.flush == 0 || kb + 1 == nkb) {                    // partial complete -> accumulation warps
@@ -750,23 +774,26 @@ static int act_dtype_of(int precision) {
 }
 
 int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int cout, int cin, int kh, int kw, int stride,
-                         int pad, int in_dtype, bool has_prologue, int out_nchw, cudaStream_t st) {
+                         int pad, int in_dtype, bool has_prologue, int out_nchw, bool in_interleaved, cudaStream_t st) {
   u.eligible = false;
   u.enabled = false;
+  u.c32i = false;
   if (precision == YOLO_PREC_FP32) return YOLO_OK;
   const char* dis = getenv("YOLO_B200_DISABLE_UMMA");
   if (dis && dis[0] == '1') return YOLO_OK;
   // shapes the tensor-core kernel takes; everything else stays on the FFMA kernel
   if (cin % 32 != 0 || has_prologue || out_nchw || kh != kw || in_dtype != act_dtype_of(precision)) return YOLO_OK;
   if (stride < 1 || stride > 8 || pad > 127) return YOLO_OK;
+  if (in_interleaved && (precision != YOLO_PREC_FP16X3 || cin != 32)) return YOLO_OK;      // only the C32I kernel reads that layout
+  u.c32i = in_interleaved;
   const int np = planes_of(precision);
   u.precision = precision; u.cout = cout; u.cin = cin; u.kh = kh; u.kw = kw; u.stride = stride; u.pad = pad;
-  u.bk = cin % 64 == 0 ? 64 : 32;
-  if (const char* be = getenv("YOLO_B200_BK")) { if (atoi(be) == 32) u.bk = 32; }      // experiment: more, smaller pipeline stages
+  u.bk = (cin % 64 == 0 || u.c32i) ? 64 : 32;
+  if (const char* be = getenv("YOLO_B200_BK")) { if (atoi(be) == 32 && !u.c32i) u.bk = 32; }      // experiment: more, smaller pipeline stages
   u.bn_tile = pick_bn(cout);
   const int n_tiles_n = (cout + u.bn_tile - 1) / u.bn_tile;
   const int rows = n_tiles_n * u.bn_tile;                  // zero padded so a weight tile never crosses a plane
-  const size_t K = (size_t)kh * kw * cin;
+  const size_t K = (size_t)kh * kw * (u.c32i ? 64 : cin);     // C32I: K' = 64 per tap ([hi | lo] activation rows)
   std::vector<unsigned short> host((size_t)np * rows * K, 0);
   // fp16 planes: scale the weights by a power of two so that max|w| lands in [256, 512): the low plane (2^-12 of the
   // value, stored unscaled) then stays a NORMAL fp16 number for all but negligible weights.  Exact; undone in the epilogue.
@@ -774,7 +801,7 @@ int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int co
   u.acc_scale = 1.f;
   if (precision == YOLO_PREC_FP16X3) {
     float wmax = 0.f;
-    for (size_t i = 0; i < (size_t)cout * K; ++i) wmax = fmaxf(wmax, fabsf(w_oihw[i]));
+    for (size_t i = 0; i < (size_t)cout * cin * kh * kw; ++i) wmax = fmaxf(wmax, fabsf(w_oihw[i]));
     if (wmax > 0.f && std::isfinite(wmax)) {
       int e;
       frexpf(wmax, &e);                                     // wmax = f * 2^e, f in [0.5, 1)
@@ -790,7 +817,13 @@ int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int co
         for (int s = 0; s < kw; ++s) {
           float v = w_oihw[(((size_t)o * cin + c) * kh + r) * kw + s] * prescale;
           const size_t k = (size_t)(r * kw + s) * cin + c;
-          if (precision == YOLO_PREC_FP16X3) {
+          if (u.c32i) {                                     // plane X = [w_hi | w_hi], plane Y = [w_lo | 0]
+            const size_t k2 = (size_t)(r * kw + s) * 64 + c;
+            unsigned short h0 = f2h(v);
+            host[((size_t)0 * rows + o) * K + k2] = h0;
+            host[((size_t)0 * rows + o) * K + k2 + 32] = h0;
+            host[((size_t)1 * rows + o) * K + k2] = f2h(v - h2f(h0));
+          } else if (precision == YOLO_PREC_FP16X3) {
             unsigned short h0 = f2h(v);
             host[((size_t)0 * rows + o) * K + k] = h0;
             host[((size_t)1 * rows + o) * K + k] = f2h((v - h2f(h0)) * kF16LoScale);
@@ -819,14 +852,14 @@ int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int co
                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(YOLO_E_CUDA, "cuTensorMapEncodeTiled(weights %dx%zu) failed: %d", np * rows, K, (int)cr);
   u.has_map_b2 = false;
-  if (u.bn_tile % 32 == 0) {                               // half-height box for the 2-CTA path (each CTA stages BN/2 weight rows)
+  if (u.bn_tile % 32 == 0 && !u.c32i) {                    // half-height box for the 2-CTA path (each CTA stages BN/2 weight rows)
     cuuint32_t box2[2] = {(cuuint32_t)u.bk, (cuuint32_t)(u.bn_tile / 2)};
     cr = g_encode_tiled(reinterpret_cast<CUtensorMap*>(u.map_b2), dt, 2, u.w_packed, gdim, gstr, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     u.has_map_b2 = cr == CUDA_SUCCESS;
   }
   u.has_map_bw = false;
-  if (u.bk == 64 && cout % 256 == 0 && precision != YOLO_PREC_BF16X6) {      // 256-row box for the 128 x 256 tiles
+  if (u.bk == 64 && cout % 256 == 0 && precision != YOLO_PREC_BF16X6 && !u.c32i) {      // 256-row box for the 128 x 256 tiles
     cuuint32_t boxw[2] = {(cuuint32_t)u.bk, 256u};
     cr = g_encode_tiled(reinterpret_cast<CUtensorMap*>(u.map_bw), dt, 2, u.w_packed, gdim, gstr, boxw, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -841,9 +874,10 @@ int umma_build_maps(UmmaConv& u, void* in_base, int max_batch, int H, int W, int
   if (!u.eligible) return YOLO_OK;
   int rc = load_driver_entry_points();
   if (rc) return rc;
-  const int np = planes_of(u.precision);
+  const int np = u.c32i ? 1 : planes_of(u.precision);       // C32I: both planes sit in one 64-element pixel row
+  if (u.c32i && (cpitch != 64 || coff != 0)) return YOLO_OK;
   if (cpitch % 8 != 0 || (reinterpret_cast<uintptr_t>(in_base) & 15)) return YOLO_OK;       // TMA stride/address alignment
-  (void)C; (void)coff;
+  (void)C;
   const CUtensorMapDataType dt = u.precision == YOLO_PREC_FP16X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapSwizzle sw = u.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   u.a_tiled = false;
@@ -926,6 +960,7 @@ static int launch_mode(const UmmaConv& u, const UmmaParams& p, int smem_bytes, c
     if (p.dual == 6 && p.out_dtype != DT_F32) return launch_mode3<MODE, false, 6>(u, p, smem_bytes, st);
   }
   if constexpr (MODE == 2) {
+    if (p.dual == 7) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 7>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 7>(u, p, smem_bytes, st);
     if (p.dual == 4) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 4>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 4>(u, p, smem_bytes, st);
     if (p.dual == 3) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 3>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 3>(u, p, smem_bytes, st);
     if (p.dual == 1) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 1>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 1>(u, p, smem_bytes, st);
@@ -952,7 +987,7 @@ static int launch_range(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, i
   p.bk = u.bk;
   p.n_tiles_n = (d.Cout + p.BN - 1) / p.BN;
   p.n_tiles = ((p.M + TILE_M - 1) / TILE_M) * p.n_tiles_n;
-  p.taps = d.kh * d.kw; p.kw = d.kw; p.cin_blocks = d.Cin / p.bk;
+  p.taps = d.kh * d.kw; p.kw = d.kw; p.cin_blocks = u.c32i ? 1 : d.Cin / p.bk;
   p.Ho = d.Ho; p.Wo = d.Wo; p.stride = d.stride; p.pad = d.pad;
   p.in_coff = d.in_coff;
   p.a_plane_n = u.max_batch;
@@ -987,12 +1022,13 @@ static int launch_range(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, i
     p.n_tiles_n = d.Cout / 256;
     p.n_tiles = m_tiles * p.n_tiles_n;
   }
+  if (u.c32i) p.dual = 7;
   // wide pairs (KIND 6): 256 x 256 per CTA pair (EXPERIMENT: YOLO_B200_PAIRWIDE=1)
   const char* pw = getenv("YOLO_B200_PAIRWIDE");
   if (p.dual == 5 && m_tiles >= 2 && u.bn_tile == 128 && pw && pw[0] == '1') p.dual = 6;
   if (p.dual == 3) p.n_tiles_n /= 2;                                    // scheduling units per row of the tile grid
-  if (p.dual && p.dual != 5) p.n_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
-  const int stage_bytes = np * ((p.dual == 1 ? 2 : 1) * TILE_M * p.bk * 2 + (p.dual == 3 ? 2 : 1) * ((p.dual == 2 || p.dual == 3 || p.dual == 6) ? p.BN / 2 : p.BN) * p.bk * 2);
+  if (p.dual && p.dual != 5 && p.dual != 7) p.n_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
+  const int stage_bytes = p.dual == 7 ? TILE_M * p.bk * 2 + np * p.BN * p.bk * 2 : np * ((p.dual == 1 ? 2 : 1) * TILE_M * p.bk * 2 + (p.dual == 3 ? 2 : 1) * ((p.dual == 2 || p.dual == 3 || p.dual == 6) ? p.BN / 2 : p.BN) * p.bk * 2);
   const int aux_bytes = 16 * MAX_STAGES + 128 + 2 * 2 * p.BN * 4 + 64;
   // 8 MMAs of the leading product per TMEM partial.  Longer partials are ~3 % faster but their truncation bias is
   // systematic (same sign on every output) and compounds through the layers: flush 8 -> Darknet-53 head error 6.6e-4
@@ -1000,7 +1036,8 @@ static int launch_range(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, i
   p.flush = p.bk == 64 ? 2 : 4;
   // merged accumulation (default): every plane pair accumulates in the partial buffer, correction products first, one
   // k-block per partial.  Measured better AND faster than the separate correction accumulator (r1_ncu_summary.md).
-  if (p.dual == 5 || p.dual == 6) p.flush = 1;                                          // merged accumulation: one k-block (12 MMAs) per partial
+  if (p.dual == 5 || p.dual == 6) p.flush = 1;
+  if (p.dual == 7) p.flush = 4;                                          // two hi*hi MMAs per tap -> 8 per partial                                          // merged accumulation: one k-block (12 MMAs) per partial
   if (const char* de2 = getenv("YOLO_B200_DBG_PAIRS")) p.dbg_pairs = atoi(de2);
   if (const char* pf = getenv("YOLO_B200_PREFETCH")) p.prefetch = atoi(pf);
   if (const char* fe = getenv("YOLO_B200_FLUSH")) { int f = atoi(fe); if (f >= 1 && f <= 64) p.flush = f; }

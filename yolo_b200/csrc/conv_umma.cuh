@@ -22,11 +22,12 @@ struct UmmaConv {
   bool a_tiled = false;       // 1x1 conv: map_a is a tiled 2-D map over [pixels][channels]
   long long a_plane_rows = 0;
   int max_batch = 0;
+  bool c32i = false;          // Cin = 32, plane-interleaved activations ([hi(32) | lo(32)] per pixel): KIND 7
   float acc_scale = 1.f;     // 2^-s: the packed weights are pre-scaled by 2^s (fp16 planes stay normal), undone in the epilogue
 };
 
 int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int cout, int cin, int kh, int kw, int stride,
-                         int pad, int in_dtype, bool has_prologue, int out_nchw, cudaStream_t st);
+                         int pad, int in_dtype, bool has_prologue, int out_nchw, bool in_interleaved, cudaStream_t st);
 int umma_build_maps(UmmaConv& u, void* in_base, int max_batch, int H, int W, int C, int cpitch, int coff);
 int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st);
 void umma_release(UmmaConv& u);

@@ -75,7 +75,9 @@ struct Builder {
     add_param(name + ".running_var", {c});
     return i;
   }
-  View new_buffer(int H, int W, int C, int dtype) {
+  // interleave: both fp16 planes of a pixel in one 2C-element row (plane stride C) - the layout the Cin = 32 tensor-core
+  // kernel reads as single 128-byte rows (conv_umma.cu KIND 7); every other kernel just sees (cpitch, plane stride)
+  View new_buffer(int H, int W, int C, int dtype, bool interleave = false) {
     Buffer b;
     b.dtype = dtype;
     b.bytes_per_image = (size_t)H * W * C * dtype_bytes_per_elem(dtype);
@@ -84,6 +86,7 @@ struct Builder {
     v.buf = (int)h->bufs.size() - 1;
     v.H = H; v.W = W; v.C = C; v.cpitch = C; v.coff = 0; v.dtype = dtype;
     v.ps = (long long)h->spec.max_batch * H * W * C;
+    if (interleave) { v.cpitch = 2 * C; v.ps = C; v.il = true; }
     return v;
   }
   static View slice(const View& v, int coff, int c) {
@@ -114,7 +117,9 @@ struct Builder {
       op.out = *dst;
       op.out.H = Hd; op.out.W = Wd; op.out.C = cout;
     } else {
-      op.out = new_buffer(Hd, Wd, cout, h->act_dtype);
+      static const char* il_env = getenv("YOLO_B200_C32I");
+      const bool il = h->act_dtype == DT_F16X2 && cout == 32 && !upsample2 && !(il_env && il_env[0] == '0');
+      op.out = new_buffer(Hd, Wd, cout, h->act_dtype, il);
     }
     if (res) { op.res = *res; op.has_res = true; }
     h->flops_per_image += 2.0 * Ho * Wo * (double)cout * k * k * in.C;
@@ -481,7 +486,7 @@ extern "C" int yolo_finalize_params(yolo_handle* h, void* stream) {
   for (auto& op : h->ops) {
     if (op.kind != OP_CONV) continue;
     int rc = umma_prepare_weights(op.umma, h->spec.precision, h->params[op.p_weight].host.data(), op.cout, op.in.C, op.kh, op.kw,
-                                  op.stride, op.pad, op.in.dtype, op.pre_scale != nullptr, op.out_nchw, st);
+                                  op.stride, op.pad, op.in.dtype, op.pre_scale != nullptr, op.out_nchw, op.in.il, st);
     if (rc) return hfail(h, rc);
   }
   h->finalized = true;
@@ -599,7 +604,7 @@ extern "C" int yolo_debug_activation(yolo_handle* h, const char* layer_name, int
   YB_CUDA(cudaDeviceSynchronize());
   const size_t esz = v.dtype == DT_F32 ? 4 : 2;
   const int nplanes = dtype_planes(v.dtype);
-  const size_t nraw = (size_t)(nplanes - 1) * v.ps + (size_t)batch * v.H * v.W * v.cpitch;
+  const size_t nraw = (size_t)(nplanes - 1) * v.ps + ((size_t)batch * v.H * v.W - 1) * v.cpitch + v.coff + v.C;
   std::vector<unsigned char> raw(nraw * esz);
   YB_CUDA(cudaMemcpy(raw.data(), h->ws + h->bufs[v.buf].offset, raw.size(), cudaMemcpyDeviceToHost));
   for (int n = 0; n < batch; ++n)

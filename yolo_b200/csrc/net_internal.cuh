@@ -33,6 +33,7 @@ struct View {              // NHWC tensor or a channel slice of a wider buffer (
   int cpitch = 0, coff = 0;
   int dtype = DT_F32;
   long long ps = 0;        // plane stride in elements (DT_BF16X3: plane p lives at element offset p*ps)
+  bool il = false;         // planes interleaved per pixel: row = [plane 0 (C) | plane 1 (C)], cpitch = 2C, ps = C (32-channel fp16x2 tensors)
 };
 
 enum OpKind { OP_CONV = 0, OP_POOL = 1 };
