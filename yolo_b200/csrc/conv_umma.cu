@@ -59,6 +59,7 @@ struct UmmaParams {
   int stages;
   int flush;                                // k-blocks per TMEM partial sum (two-level accumulation)
   int dual;                                 // 1: CTA tile = two M tiles sharing the weight tile; 2: cta_group::2 pair
+  int dbg_nostore;                          // timing experiments: 1 = skip the epilogue's 16-bit stores, 2 = skip the epilogue (wrong results)
   int dbg_pairs;                            // >0: issue only the first n plane pairs (timing experiments; wrong results)
   int prefetch;                             // >0: L2-prefetch the operands of k-block kb + prefetch
   int a_tiled;                              // 1x1/s1/p0: activations are a plain [pixels][channels] matrix -> tiled TMA, not im2col
@@ -610,7 +611,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // (kept compact on purpose: the first version of this block was 17k SASS instructions and stalled on
       //  instruction fetch - profiles/r1_ncu_summary.md)
       const int m = m0 + row;
-      if (m >= p.M) continue;
+      if (m >= p.M || p.dbg_nostore == 2) continue;
       size_t pix[4];
       int npix = 1;
       if (p.upsample2) {
@@ -704,7 +705,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (pl + 1 < NP) { y[i] -= ha; y[i + 1] -= hb; }
               }
             }
-            for (int q = 0; q < npix; ++q) {
+            for (int q = 0; q < npix && !p.dbg_nostore; ++q) {
               uint4* op = reinterpret_cast<uint4*>(static_cast<unsigned short*>(p.out) + (size_t)pl * p.out_plane_stride +
                                                    pix[q] * p.out_cpitch + p.out_coff + nb);
 #pragma unroll
@@ -1039,6 +1040,7 @@ static int launch_range(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, i
   if (p.dual == 5 || p.dual == 6) p.flush = 1;
   if (p.dual == 7) p.flush = 4;                                          // two hi*hi MMAs per tap -> 8 per partial                                          // merged accumulation: one k-block (12 MMAs) per partial
   if (const char* de2 = getenv("YOLO_B200_DBG_PAIRS")) p.dbg_pairs = atoi(de2);
+  if (const char* ns = getenv("YOLO_B200_DBG_NOSTORE")) p.dbg_nostore = atoi(ns);
   if (const char* pf = getenv("YOLO_B200_PREFETCH")) p.prefetch = atoi(pf);
   if (const char* fe = getenv("YOLO_B200_FLUSH")) { int f = atoi(fe); if (f >= 1 && f <= 64) p.flush = f; }
   int stages = (SMEM_LIMIT - 1024 - aux_bytes) / stage_bytes;
