@@ -59,6 +59,7 @@ struct UmmaParams {
   int stages;
   int flush;                                // k-blocks per TMEM partial sum (two-level accumulation)
   int dual;                                 // 1: CTA tile = two M tiles sharing the weight tile; 2: cta_group::2 pair
+  int b_split;                              // wide tiles: fetch the 256 weight rows as two 128-row boxes (experiment)
   int dbg_nostore;                          // timing experiments: 1 = skip the epilogue's 16-bit stores, 2 = skip the epilogue (wrong results)
   int dbg_pairs;                            // >0: issue only the first n plane pairs (timing experiments; wrong results)
   int prefetch;                             // >0: L2-prefetch the operands of k-block kb + prefetch
@@ -399,7 +400,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               if (MCAST)
                 tma_load_2d_mc(sb + pl * b_tile_bytes + (int)cta_rank * half_rows * row_bytes, &map_b, full, kb * p.bk,
                                n0 + (int)cta_rank * half_rows + pl * p.b_plane_rows, (uint16_t)3);
-              else
+              else if (WIDE && p.b_split) {
+                tma_load_2d(sb + pl * b_tile_bytes, &map_b, full, kb * p.bk, n0 + pl * p.b_plane_rows);
+                tma_load_2d(sb + pl * b_tile_bytes + b_tile_bytes / 2, &map_b, full, kb * p.bk, n0 + 128 + pl * p.b_plane_rows);
+              } else
                 tma_load_2d(sb + pl * b_tile_bytes, &map_b, full, kb * p.bk, n0 + pl * p.b_plane_rows);
             }
           }
@@ -949,7 +953,7 @@ static int launch_mode3(const UmmaConv& u, const UmmaParams& p, int smem_bytes, 
   }
   const int grid = p.n_tiles < g_num_sms ? p.n_tiles : g_num_sms;
   conv_umma_kernel<MODE, OUT_F32, KIND><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
-                                                                               *reinterpret_cast<const CUtensorMap*>(KIND == 5 ? u.map_bw : u.map_b), p);
+                                                                               *reinterpret_cast<const CUtensorMap*>((KIND == 5 && !p.b_split) ? u.map_bw : u.map_b), p);
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
@@ -1041,6 +1045,7 @@ static int launch_range(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, i
   if (p.dual == 7) p.flush = 4;                                          // two hi*hi MMAs per tap -> 8 per partial                                          // merged accumulation: one k-block (12 MMAs) per partial
   if (const char* de2 = getenv("YOLO_B200_DBG_PAIRS")) p.dbg_pairs = atoi(de2);
   if (const char* ns = getenv("YOLO_B200_DBG_NOSTORE")) p.dbg_nostore = atoi(ns);
+  if (const char* bs = getenv("YOLO_B200_BSPLIT")) p.b_split = (bs[0] == '1' && p.dual == 5 && u.bn_tile == 128) ? 1 : 0;
   if (const char* pf = getenv("YOLO_B200_PREFETCH")) p.prefetch = atoi(pf);
   if (const char* fe = getenv("YOLO_B200_FLUSH")) { int f = atoi(fe); if (f >= 1 && f <= 64) p.flush = f; }
   int stages = (SMEM_LIMIT - 1024 - aux_bytes) / stage_bytes;

@@ -234,6 +234,81 @@ wgrad_kernel(const float* __restrict__ x, int N, int H, int W, int Cin, int x_cp
   }
 }
 
+// Same contraction with a 128 x 128 output tile, 8 x 8 outputs per thread, float4 gathers (NHWC fp32 input, Cin % 4 == 0,
+// Cout % 4 == 0) and register prefetch of the next pixel chunk: 16 FMAs per shared-memory load instead of 2.
+__global__ void __launch_bounds__(256)
+wgrad128_kernel(const float* __restrict__ x, int N, int H, int W, int Cin, int x_cpitch, int x_coff, const float* __restrict__ dz,
+                int Ho, int Wo, int Cout, int kh, int kw, int stride, int pad, float* __restrict__ dW, int cout_pad) {
+  constexpr int TK = 128, TN = 128, TM = 16;
+  __shared__ __align__(16) float As[TM][TK];
+  __shared__ __align__(16) float Ds[TM][TN];
+  const int K = kh * kw * Cin, M = N * Ho * Wo, HoWo = Ho * Wo;
+  const int k0 = blockIdx.x * TK, n0 = blockIdx.y * TN;
+  const int slab = (M + gridDim.z - 1) / gridDim.z;
+  const int m_begin = blockIdx.z * slab, m_end = min(M, m_begin + slab);
+  const int tid = threadIdx.x, tk = tid >> 4, tn = tid & 15;        // 16 x 16 threads, 8 x 8 outputs each (two 4-wide halves)
+  // loader role: float4 column lc of pixel rows lr and lr + 8 of every chunk; the k / n decode is loop invariant
+  const int lr = tid >> 5, lc = (tid & 31) * 4;
+  const int k = k0 + lc, nn = n0 + lc;
+  const bool k_ok = k < K, n_ok = nn < Cout;
+  int r = 0, sx = 0, c = 0;
+  if (k_ok) { const int tap = k / Cin; c = k - tap * Cin; r = tap / kw; sx = tap - r * kw; }
+  auto gather = [&](int m, float4& a, float4& d) {
+    a = make_float4(0.f, 0.f, 0.f, 0.f);
+    d = a;
+    if (m < m_end) {
+      if (k_ok) {
+        const int n = m / HoWo, rem = m - n * HoWo, oh = rem / Wo, ow = rem - oh * Wo;
+        const int ih = oh * stride - pad + r, iw = ow * stride - pad + sx;
+        if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+          a = __ldg(reinterpret_cast<const float4*>(x + ((size_t)(n * H + ih) * W + iw) * x_cpitch + x_coff + c));
+      }
+      if (n_ok) d = __ldg(reinterpret_cast<const float4*>(dz + (size_t)m * Cout + nn));
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float4 pa[2], pd[2];
+  gather(m_begin + lr, pa[0], pd[0]);
+  gather(m_begin + lr + 8, pa[1], pd[1]);
+  for (int mb = m_begin; mb < m_end; mb += TM) {
+    *reinterpret_cast<float4*>(&As[lr][lc]) = pa[0];
+    *reinterpret_cast<float4*>(&As[lr + 8][lc]) = pa[1];
+    *reinterpret_cast<float4*>(&Ds[lr][lc]) = pd[0];
+    *reinterpret_cast<float4*>(&Ds[lr + 8][lc]) = pd[1];
+    __syncthreads();
+    if (mb + TM < m_end) {                                          // prefetch the next chunk while this one is multiplied
+      gather(mb + TM + lr, pa[0], pd[0]);
+      gather(mb + TM + lr + 8, pa[1], pd[1]);
+    }
+#pragma unroll
+    for (int ml = 0; ml < TM; ++ml) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[ml][tk * 4]), a1 = *reinterpret_cast<const float4*>(&As[ml][64 + tk * 4]);
+      const float4 d0 = *reinterpret_cast<const float4*>(&Ds[ml][tn * 4]), d1 = *reinterpret_cast<const float4*>(&Ds[ml][64 + tn * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], d[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int kk = k0 + (i >> 2) * 64 + tk * 4 + (i & 3);
+    if (kk >= K) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j >> 2) * 64 + tn * 4 + (j & 3);
+      if (n < Cout) atomicAdd(&dW[(size_t)kk * cout_pad + n], acc[i][j]);
+    }
+  }
+}
+
 // wT[((kh-1-r)*kw + (kw-1-s))*Cout + o][c] = W[(r*kw+s)*Cin + c][o]
 __global__ void wflip_kernel(const float* __restrict__ Wm, int kh, int kw, int Cin, int Cout, int cout_pad, float* __restrict__ wT, int cin_pad) {
   const size_t total = (size_t)kh * kw * Cin * Cout;
@@ -497,7 +572,16 @@ extern "C" int yolo_train_forward_backward(yolo_handle* h, const void* input, in
     const int K = op.kh * op.kw * op.in.C;
     int slabs = std::max(1, std::min(M / 512, 64));
     dim3 gw((K + 63) / 64, (C + 63) / 64, slabs);
-    wgrad_kernel<<<gw, 256, 0, st>>>(act_ptr(h, op.in, input), batch, op.in.H, op.in.W, op.in.C, op.in.cpitch, op.in.coff,
+    const float* xin = act_ptr(h, op.in, input);
+    if (op.in.buf != -1 && op.in.C % 4 == 0 && op.in.cpitch % 4 == 0 && op.in.coff % 4 == 0 && C % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(xin) & 15) == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0) {
+      const int tiles = ((K + 127) / 128) * ((C + 127) / 128);
+      int slabs2 = std::max(1, std::min(M / 256, std::max(1, 592 / tiles)));          // ~4 CTAs per SM in total
+      dim3 gw2((K + 127) / 128, (C + 127) / 128, slabs2);
+      wgrad128_kernel<<<gw2, 256, 0, st>>>(xin, batch, op.in.H, op.in.W, op.in.C, op.in.cpitch, op.in.coff, dz, L.Ho, L.Wo, C, op.kh, op.kw,
+                                           op.stride, op.pad, T->G + L.o_w, op.cout_pad);
+    } else
+    wgrad_kernel<<<gw, 256, 0, st>>>(xin, batch, op.in.H, op.in.W, op.in.C, op.in.cpitch, op.in.coff,
                                      op.in.buf == -1 ? lay_in : 0, dz, L.Ho, L.Wo, C, op.kh, op.kw, op.stride, op.pad, T->G + L.o_w, op.cout_pad);
     ++g_launches;
     // data gradient (not needed for the network input)
