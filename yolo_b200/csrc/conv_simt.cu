@@ -99,7 +99,7 @@ __device__ __forceinline__ void store4(__half* p, const float v[4]) {
 __device__ __forceinline__ void store1(__half* p, float v) { *p = __float2half_rn(v); }
 
 // ---- storage formats ---------------------------------------------------------------------------------------
-// F32 / BF16: one plane.  BF16X3: v = p0 + p1 + p2 (exact 24-bit split).  F16X2: v = p0 + p1 * 2^-11 (22-bit split);
+// F32 / BF16: one plane.  BF16X3: v = p0 + p1 + p2 (exact 24-bit split).  F16X2: v = p0 + p1 (22-bit fp16 split, p1 unscaled);
 // plane q lives at element offset q * plane_stride.
 struct FmtF32 { using T = float; static constexpr int NP = 1; static constexpr int ALIGN = 4; };
 struct FmtBF16 { using T = __nv_bfloat16; static constexpr int NP = 1; static constexpr int ALIGN = 8; };

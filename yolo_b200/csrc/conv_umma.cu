@@ -12,23 +12,20 @@
 //
 // Precision modes (template MODE):
 //   MODE 0  bf16: one operand plane, fp32 accumulate.
-//   MODE 2  "fp16x3": every fp32 operand value is carried as two fp16 planes v = v0 + v1 * 2^-11 (22-bit split; v1
-//           stored pre-scaled so it stays a normal fp16 number).  Three plane pairs are multiplied: (0,0) into the
-//           rotating main accumulators, (0,1) and (1,0) into the correction accumulator which the epilogue scales by
-//           2^-11.  The dropped (1,1) pair is 2^-22 relative - the accuracy class of "3xTF32" at twice its rate.
+//   MODE 2  "fp16x3": every fp32 operand value is carried as two fp16 planes v = v0 + v1 (22-bit split; v1 unscaled - see
+//           common.cuh - and the weights pre-scaled by a power of two so that their v1 stays a normal fp16 number).  Three
+//           plane pairs are multiplied: (0,0) = the leading product, (0,1) and (1,0) = corrections of 2^-11 relative size.
+//           The dropped (1,1) pair is 2^-22 relative - the accuracy class of "3xTF32" at twice its rate.
 //   MODE 1  "bf16x6": every fp32 operand value v is carried as three bf16 planes v = v0 + v1 + v2 (exact
 //           24-bit split, written by the producing layer's epilogue / packed once for the weights) and the
 //           product is formed from the six plane pairs with i + j <= 2.  Dropped pairs are <= 2^-24 relative:
 //           fp32-grade operands at 1/6 of the bf16 rate.  The tensor core's fp32 accumulator TRUNCATES (measured:
 //           a round-toward-zero bias of ~1e-8 of |acc| per MMA, i.e. -3.4e-5 relative at K = 9216 when all six
-//           pairs share one accumulator - profiles/r1_umma_precision.txt), so the leading a0*b0 products rotate
-//           over three TMEM accumulators by k-block and the five correction pairs go to a fourth; the epilogue
-//           adds the four in fp32 round-to-nearest.  That cuts the truncation steps on the leading term 18x.
+//           pairs share one accumulator - profiles/r1_umma_precision.txt): see "two-level accumulation" below.
 //
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation),
-// warps 2..5 = epilogue (TMEM -> registers -> global).  With NP = 1 the accumulator is double-buffered in
-// TMEM so the epilogue of tile i overlaps the main loop of tile i+1; with NP = 3 the four accumulators fill
-// the 512 TMEM columns (the main loop is 6x longer, the exposed epilogue is a few percent).
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2..5 and 6..9 = two
+// accumulation/epilogue groups (TMEM partial sums -> fp32 registers -> epilogue -> global); tile kinds and the accumulation
+// protocol are described at the kernel.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
@@ -223,14 +220,18 @@ __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(_
 // ---------------------------------------------------------------------------------------------------
 // Two-level accumulation.  The tensor core's fp32 accumulator truncates (round toward zero: a bias of ~1e-8 of
 // |acc| per MMA, measured in profiles/r1_umma_precision.txt), which after thousands of MMAs per output is 10-40x the
-// rounding noise of an fp32 FMA chain.  So a TMEM accumulator only ever holds a short PARTIAL sum (p.flush k-blocks =
-// 8 MMAs of the leading product); the accumulation warps add each partial into fp32 REGISTERS with round-to-nearest
-// while the MMA warp already fills the other TMEM partial buffer.  The small correction products of the split
-// precisions (2^-11 / 2^-8 of the result) may accumulate in TMEM over the whole K: their truncation is negligible.
+// rounding noise of an fp32 FMA chain, and systematic.  So a TMEM accumulator only ever holds a short PARTIAL sum; the
+// accumulation warps add each partial into fp32 REGISTERS with round-to-nearest while the MMA warp already fills the other
+// TMEM partial buffer.
+//   128-column tiles: partial = p.flush k-blocks (8 MMAs) of the leading product; the small correction products of the split
+//     precisions (2^-11 / 2^-8 of the result) accumulate in a separate TMEM accumulator over the whole K (their truncation
+//     is negligible) that is read once per tile.  The two groups alternate tiles: while one converts/stores tile i from its
+//     registers, the other one already accumulates the partials of tile i+1 - the epilogue is fully overlapped.
+//   128 x 256 tiles (WIDE): the two 256-column partial buffers fill the TMEM, so all plane pairs accumulate in the partial
+//     ("merged"), correction pairs first while the partial is still tiny, one k-block per partial.  Both groups work on every
+//     tile (128 columns each); the MMA warp runs at most two partials into the next tile while they store.
 //
 // Warps: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = accumulation/epilogue group 0, 6..9 = group 1.
-// Groups alternate tiles: while one group converts/stores tile i from its registers, the other one is already
-// accumulating the partials of tile i+1 - the epilogue is fully overlapped with the main loop.
 constexpr int GROUP_THREADS = 128;
 
 // DUAL: the CTA tile is 256 x BN = two 128-row M tiles that share every weight tile in shared memory (the main loop
