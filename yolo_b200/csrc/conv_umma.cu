@@ -56,6 +56,7 @@ struct UmmaParams {
   int stages;
   int flush;                                // k-blocks per TMEM partial sum (two-level accumulation)
   int dual;                                 // 1: CTA tile = two M tiles sharing the weight tile; 2: cta_group::2 pair
+  int hh_last;                              // merged kinds: partial = 2 k-blocks, correction products of both first (experiment)
   int b_split;                              // wide tiles: fetch the 256 weight rows as two 128-row boxes (experiment)
   int dbg_nostore;                          // timing experiments: 1 = skip the epilogue's 16-bit stores, 2 = skip the epilogue (wrong results)
   int dbg_pairs;                            // >0: issue only the first n plane pairs (timing experiments; wrong results)
@@ -421,8 +422,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t phase = 0;
       int it = 0;
       uint32_t pcount = 0;                                                     // partial buffers handed out so far
+      // sel: 0 = all plane pairs, 1 = correction pairs only, 2 = leading pair only (hh-last ordering over two k-blocks)
       auto issue_pairs = [&](uint32_t sa_tile, uint32_t sb, uint32_t tmem_main, uint32_t tmem_corr, uint32_t& main_written,
-                             uint32_t& corr_written) {
+                             uint32_t& corr_written, int sel = 0) {
         if constexpr (C32I) {
           const uint64_t adesc = make_smem_desc(sa_tile, row_bytes);
           const uint64_t bx = make_smem_desc(sb, row_bytes), by = make_smem_desc(sb + b_tile_bytes, row_bytes);
@@ -444,6 +446,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           // their additions do not add full-magnitude truncation steps; the leading product closes the partial
           const int pair = MERGE ? N_PAIRS - 1 - pi : pi;
           if (p.dbg_pairs != 0 && pair >= p.dbg_pairs) continue;          // timing experiments (-1: no MMA at all, fill + drain only)
+          if ((sel == 1 && pair == 0) || (sel == 2 && pair != 0)) continue;
           // pair 0 = leading product (plane 0 x plane 0) -> partial buffer; the rest -> correction accumulator
           constexpr int PA6[6] = {0, 0, 1, 0, 1, 2}, PB6[6] = {0, 1, 0, 2, 1, 0};
           constexpr int PA3[3] = {0, 0, 1}, PB3[3] = {0, 1, 0};
@@ -478,6 +481,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t tmem_corr = tmem_base + (2 + cbuf) * acc_stride;
           uint32_t corr_written = 0, tmem_main = 0, main_written = 0;
           int pbuf = 0;
+          if (MERGE && p.hh_last) {
+            // EXPERIMENT (YOLO_B200_HHLAST=1): one partial = two k-blocks, the correction products of BOTH first, then the
+            // leading products - half the TMEM drains of flush 1 with 8 instead of 16 full-magnitude truncation steps
+            for (int kb = 0; kb < nkb; kb += 2) {
+              pbuf = pcount & 1;
+              mbar_wait(bar_pempty + 8 * pbuf, ((pcount >> 1) & 1) ^ 1);
+              tc_fence_after();
+              tmem_main = tmem_base + pbuf * acc_stride;
+              main_written = 0;
+              const int n2 = nkb - kb < 2 ? nkb - kb : 2;
+              int sj[2];
+              uint32_t pj[2];
+              for (int j = 0; j < n2; ++j) {
+                sj[j] = stage + j; pj[j] = phase;
+                if (sj[j] >= p.stages) { sj[j] -= p.stages; pj[j] ^= 1; }
+                mbar_wait(bar_full + 8 * sj[j], pj[j]);
+                tc_fence_after();
+                const uint32_t sa = smem_base + sj[j] * stage_bytes;
+                issue_pairs(sa, sa + NPA * A_TILE_BYTES, tmem_main, tmem_corr, main_written, corr_written, 1);
+              }
+              for (int j = 0; j < n2; ++j) {
+                const uint32_t sa = smem_base + sj[j] * stage_bytes;
+                issue_pairs(sa, sa + NPA * A_TILE_BYTES, tmem_main, tmem_corr, main_written, corr_written, 2);
+                commit_stage(bar_empty + 8 * sj[j]);
+              }
+              stage += n2;
+              if (stage >= p.stages) { stage -= p.stages; phase ^= 1; }
+              commit(bar_pfull + 8 * pbuf);
+              ++pcount;
+            }
+          } else
           for (int kb = 0; kb < nkb; ++kb) {
             if (kb % p.flush == 0) {                                           // start a new partial sum
               pbuf = pcount & 1;
@@ -1029,9 +1063,11 @@ static int launch_range(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, i
     p.n_tiles = m_tiles * p.n_tiles_n;
   }
   if (u.c32i) p.dual = 7;
-  // wide pairs (KIND 6): 256 x 256 per CTA pair (EXPERIMENT: YOLO_B200_PAIRWIDE=1)
+  // wide pairs (KIND 6, default where at least two M tiles exist; YOLO_B200_PAIRWIDE=0 keeps the single-CTA wide tiles):
+  // 256 x 256 per CTA pair, each CTA stages half of the weight rows -> a third less fill per SM and three pipeline stages.
+  // Pays off only together with two-k-block partials in hh-last order (below): every partial hand-off crosses the cluster.
   const char* pw = getenv("YOLO_B200_PAIRWIDE");
-  if (p.dual == 5 && m_tiles >= 2 && u.bn_tile == 128 && pw && pw[0] == '1') p.dual = 6;
+  if (p.dual == 5 && mt_count <= 0 && m_tiles >= 2 && u.bn_tile == 128 && !(pw && pw[0] == '0')) p.dual = 6;
   if (p.dual == 3) p.n_tiles_n /= 2;                                    // scheduling units per row of the tile grid
   if (p.dual && p.dual != 5 && p.dual != 7) p.n_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
   const int stage_bytes = p.dual == 7 ? TILE_M * p.bk * 2 + np * p.BN * p.bk * 2 : np * ((p.dual == 1 ? 2 : 1) * TILE_M * p.bk * 2 + (p.dual == 3 ? 2 : 1) * ((p.dual == 2 || p.dual == 3 || p.dual == 6) ? p.BN / 2 : p.BN) * p.bk * 2);
@@ -1046,6 +1082,14 @@ static int launch_range(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, i
   if (p.dual == 7) p.flush = 4;                                          // two hi*hi MMAs per tap -> 8 per partial                                          // merged accumulation: one k-block (12 MMAs) per partial
   if (const char* de2 = getenv("YOLO_B200_DBG_PAIRS")) p.dbg_pairs = atoi(de2);
   if (const char* ns = getenv("YOLO_B200_DBG_NOSTORE")) p.dbg_nostore = atoi(ns);
+  // hh-last partials (default on the pair kind): one partial = two k-blocks, the correction products of both first, then the
+  // leading ones.  Measured (3x3 512->1024 @26^2): KIND 6 587 -> 503 us, KIND 5 589 -> 590 us (it has only two stages to hold);
+  // Darknet-53 head error 2.4e-4 -> 2.7e-4, step 14.9 -> 13.8 ms.  YOLO_B200_HHLAST=0|1 overrides.
+  {
+    const char* hl = getenv("YOLO_B200_HHLAST");
+    const bool on = hl ? hl[0] == '1' : p.dual == 6;
+    if (on && (p.dual == 5 || p.dual == 6)) { p.hh_last = 1; p.flush = 2; }
+  }
   if (const char* bs = getenv("YOLO_B200_BSPLIT")) p.b_split = (bs[0] == '1' && p.dual == 5 && u.bn_tile == 128) ? 1 : 0;
   if (const char* pf = getenv("YOLO_B200_PREFETCH")) p.prefetch = atoi(pf);
   if (const char* fe = getenv("YOLO_B200_FLUSH")) { int f = atoi(fe); if (f >= 1 && f <= 64) p.flush = f; }
@@ -1079,7 +1123,7 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st) {
   const char* we = getenv("YOLO_B200_WIDE");
   const char* se = getenv("YOLO_B200_SPLIT");
   const bool wide_ok = u.enabled && u.has_map_bw && d.out_dtype != DT_F32 && !(we && we[0] == '0') && !getenv("YOLO_B200_DUAL") &&
-                       !getenv("YOLO_B200_PAIR") && !getenv("YOLO_B200_MCAST") && !getenv("YOLO_B200_PAIRWIDE");
+                       !getenv("YOLO_B200_PAIR") && !getenv("YOLO_B200_MCAST");
   if (!wide_ok || !(se && se[0] == '1')) return launch_range(u, d, st, 0, 0, true);
   if (g_num_sms == 0) {
     int dev = 0;
