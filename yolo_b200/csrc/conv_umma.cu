@@ -275,7 +275,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // MERGE (wide tiles, whose two 256-column partial buffers fill the TMEM): every plane pair accumulates in the partial
   // buffer, correction products first.  The 128-column kinds keep the separate correction accumulator: measured 7 %
   // faster there (two independent accumulation chains) at the same accuracy.
-  constexpr bool MERGE = WIDE;
+  constexpr bool MERGE = WIDE || KIND == 8;                       // KIND 8: KIND 0 with merged accumulation (experiment)
   constexpr bool HAS_CORR = MODE != 0 && !MERGE;
   const int A_TILE_BYTES = TILE_M * p.bk * 2;
   const int row_bytes = p.bk * 2;
@@ -1001,6 +1001,7 @@ static int launch_mode(const UmmaConv& u, const UmmaParams& p, int smem_bytes, c
   }
   if constexpr (MODE == 2) {
     if (p.dual == 7) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 7>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 7>(u, p, smem_bytes, st);
+    if (p.dual == 8) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 8>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 8>(u, p, smem_bytes, st);
     if (p.dual == 4) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 4>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 4>(u, p, smem_bytes, st);
     if (p.dual == 3) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 3>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 3>(u, p, smem_bytes, st);
     if (p.dual == 1) return p.out_dtype == DT_F32 ? launch_mode3<MODE, true, 1>(u, p, smem_bytes, st) : launch_mode3<MODE, false, 1>(u, p, smem_bytes, st);
@@ -1069,7 +1070,9 @@ static int launch_range(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, i
   const char* pw = getenv("YOLO_B200_PAIRWIDE");
   if (p.dual == 5 && mt_count <= 0 && m_tiles >= 2 && u.bn_tile == 128 && !(pw && pw[0] == '0')) p.dual = 6;
   if (p.dual == 3) p.n_tiles_n /= 2;                                    // scheduling units per row of the tile grid
-  if (p.dual && p.dual != 5 && p.dual != 7) p.n_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
+  // EXPERIMENT (YOLO_B200_NARROWMERGE=1): merged accumulation + hh-last partials on the 128-column tiles as well
+  if (const char* nm = getenv("YOLO_B200_NARROWMERGE")) { if (nm[0] == '1' && p.dual == 0 && mode_of(u.precision) == 2 && p.bk == 64) p.dual = 8; }
+  if (p.dual && p.dual != 5 && p.dual != 7 && p.dual != 8) p.n_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
   const int stage_bytes = p.dual == 7 ? TILE_M * p.bk * 2 + np * p.BN * p.bk * 2 : np * ((p.dual == 1 ? 2 : 1) * TILE_M * p.bk * 2 + (p.dual == 3 ? 2 : 1) * ((p.dual == 2 || p.dual == 3 || p.dual == 6) ? p.BN / 2 : p.BN) * p.bk * 2);
   const int aux_bytes = 16 * MAX_STAGES + 128 + 2 * 2 * p.BN * 4 + 64;
   // 8 MMAs of the leading product per TMEM partial.  Longer partials are ~3 % faster but their truncation bias is
@@ -1087,8 +1090,8 @@ static int launch_range(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, i
   // Darknet-53 head error 2.4e-4 -> 2.7e-4, step 14.9 -> 13.8 ms.  YOLO_B200_HHLAST=0|1 overrides.
   {
     const char* hl = getenv("YOLO_B200_HHLAST");
-    const bool on = hl ? hl[0] == '1' : p.dual == 6;
-    if (on && (p.dual == 5 || p.dual == 6)) { p.hh_last = 1; p.flush = 2; }
+    const bool on = hl ? hl[0] == '1' : (p.dual == 6 || p.dual == 8);
+    if (on && (p.dual == 5 || p.dual == 6 || p.dual == 8)) { p.hh_last = 1; p.flush = 2; }
   }
   if (const char* bs = getenv("YOLO_B200_BSPLIT")) p.b_split = (bs[0] == '1' && p.dual == 5 && u.bn_tile == 128) ? 1 : 0;
   if (const char* pf = getenv("YOLO_B200_PREFETCH")) p.prefetch = atoi(pf);
