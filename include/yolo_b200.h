@@ -147,6 +147,11 @@ int  yolo_output_shape(const yolo_handle* h, int index, int32_t shape[4], int32_
 int  yolo_forward(yolo_handle* h, const void* input, int batch, int in_layout,
                   void* const* outputs, void* stream);
 
+/* fp16x3 range check.  The 16-bit activation format of YOLO_PREC_FP16X3 stores v = hi + lo with an fp16 high plane: |v| > 65504
+ * saturates.  Saturation is never silent: every kernel that writes the format ORs bit 0 into a device flag of the handle
+ * (bit 1: a weight left the fp16 range when the training step re-packed it).  Reads AND CLEARS the flags; synchronises `stream`. */
+int  yolo_check_saturation(yolo_handle* h, int32_t* flags_out, void* stream);
+
 /* Debug/parity: copy an internal activation (by oracle layer name) to host as NCHW fp32. */
 int  yolo_debug_activation(yolo_handle* h, const char* layer_name, int batch, float* host_nchw, size_t n_elems);
 

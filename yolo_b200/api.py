@@ -174,7 +174,8 @@ class Net:
     def _ensure_workspace(self):
         if self._ws is None:
             n = self.lib.yolo_workspace_bytes(self._h, self.max_batch)
-            self._ws = torch.empty(max(n, 1024) + 1024, dtype=torch.uint8, device=self.device)
+            # zero-filled: tiles of the tensor-core kernels may run past the last image of a smaller batch and must read finite values
+            self._ws = torch.zeros(max(n, 1024) + 1024, dtype=torch.uint8, device=self.device)
             ptr = (self._ws.data_ptr() + 1023) & ~1023
             check(self.lib.yolo_set_workspace(self._h, C.c_void_p(ptr), n), self._h)
 
@@ -182,12 +183,26 @@ class Net:
     def _to_device(self, data):
         data = _as_tensor(data)
         if isinstance(data, np.ndarray):
+            # two pinned staging buffers, each guarded by an event recorded after its H2D copy: the host never overwrites
+            # a buffer whose asynchronous copy may still be in flight (pipelined inference / training loops)
             t = torch.from_numpy(data)
-            if self._pinned is None or self._pinned.numel() < t.numel() * t.element_size():
-                self._pinned = torch.empty(t.numel() * t.element_size(), dtype=torch.uint8).pin_memory()
-            stage = self._pinned[: t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+            nbytes = t.numel() * t.element_size()
+            if self._pinned is None:
+                self._pinned, self._pin_turn = [None, None], 0
+            i = self._pin_turn
+            self._pin_turn ^= 1
+            slot = self._pinned[i]
+            if slot is None or slot[0].numel() < nbytes:
+                slot = self._pinned[i] = [torch.empty(nbytes, dtype=torch.uint8).pin_memory(), None]
+            if slot[1] is not None:
+                slot[1].synchronize()
+            stage = slot[0][:nbytes].view(t.dtype).view(t.shape)
             stage.copy_(t)
-            return stage.to(self.device, non_blocking=True)
+            with torch.cuda.device(self.device):
+                d = stage.to(self.device, non_blocking=True)
+                slot[1] = torch.cuda.Event()
+                slot[1].record(torch.cuda.current_stream(self.device))
+            return d
         if not data.is_cuda:
             return data.to(self.device, non_blocking=True)
         return data
@@ -223,6 +238,13 @@ class Net:
             check(self.lib.yolo_predict_host(self._h, C.c_void_p(frames.data_ptr()), B, layout, rows.ctypes.data_as(C.c_void_p),
                                              idx.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)), self._h)
         return rows, idx
+
+    def saturated(self):
+        """fp16x3 range flags since the last call (bit 0: an activation exceeded 65504, bit 1: a re-packed weight did); clears them."""
+        v = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.yolo_check_saturation(self._h, C.byref(v), _stream_ptr(self.device)), self._h)
+        return int(v.value)
 
     def activation(self, name, shape):
         """Copy an internal activation (oracle layer name) to host as NCHW fp32 of the given shape (parity tests)."""

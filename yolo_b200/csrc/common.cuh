@@ -22,6 +22,10 @@ int fail(int code, const char* fmt, ...);
                       cudaGetErrorString(_e));                                            \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function attribute: set once per (function, device) - the C ABI
+// allows handles on several devices in one process (reference: one executor per context, yolo_gluon.get_ctx).
+int ensure_dyn_smem(const void* func, int bytes);
+
 // Global launch counter (kernels of THIS library), read by yolo_last_launch_count().
 extern thread_local int g_launches;
 
@@ -55,6 +59,7 @@ struct ConvDesc {
   void* out;  int out_dtype;  int Ho, Wo;  int out_cpitch, out_coff;  long long out_plane_stride;
   int upsample2;               // write every output pixel to the 2x2 block of a (2Ho, 2Wo) map
   int out_nchw;                // fp32 only: store as (N, Cout, Ho, Wo)
+  int* sat_flag;               // optional device flag: |= 1 when a value leaves the fp16 range of the DT_F16X2 high plane
 };
 
 // in_layout: 0 = NHWC of in_dtype, 1 = NCHW fp32 (stem only), 2 = NHWC uint8 scaled by 1/255 (stem only)

@@ -140,22 +140,23 @@ __device__ __forceinline__ float ld1f(const typename F::T* p, long long ps) {
 }
 // split one value into the planes of format F (returned as floats that are exactly representable in F::T)
 template <class F>
-__device__ __forceinline__ void split_planes(float v, float h[F::NP]) {
+__device__ __forceinline__ void split_planes(float v, float h[F::NP], int& sat) {
   if (F::NP == 1) { h[0] = v; return; }
   if (F::NP == 3) {
 #pragma unroll
     for (int q = 0; q < 3; ++q) { h[q] = __bfloat162float(__float2bfloat16_rn(v)); v -= h[q]; }
     return;
   }
+  if (fabsf(v) > kF16Max) sat = 1;                       // the high plane saturates: flagged (ConvDesc::sat_flag), never silent
   float c = fminf(fmaxf(v, -kF16Max), kF16Max);
   h[0] = __half2float(__float2half_rn(c));
   h[1 % F::NP] = fminf(fmaxf((v - h[0]) * kF16LoScale, -kF16Max), kF16Max);
 }
 template <class F>
-__device__ __forceinline__ void store4f(typename F::T* p, long long ps, const float v[4]) {
+__device__ __forceinline__ void store4f(typename F::T* p, long long ps, const float v[4], int& sat) {
   float h[4][F::NP];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) split_planes<F>(v[i], h[i]);
+  for (int i = 0; i < 4; ++i) split_planes<F>(v[i], h[i], sat);
 #pragma unroll
   for (int q = 0; q < F::NP; ++q) {
     const float t[4] = {h[0][q], h[1][q], h[2][q], h[3][q]};
@@ -163,9 +164,9 @@ __device__ __forceinline__ void store4f(typename F::T* p, long long ps, const fl
   }
 }
 template <class F>
-__device__ __forceinline__ void store1f(typename F::T* p, long long ps, float v) {
+__device__ __forceinline__ void store1f(typename F::T* p, long long ps, float v, int& sat) {
   float h[F::NP];
-  split_planes<F>(v, h);
+  split_planes<F>(v, h, sat);
 #pragma unroll
   for (int q = 0; q < F::NP; ++q) store1(p + q * ps, h[q]);
 }
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
   const bool vec_res = full4 && d.res && ((d.res_cpitch | d.res_coff) & 3) == 0;
   TOut* out = static_cast<TOut*>(d.out);
   const TOut* res = static_cast<const TOut*>(d.res);
+  int sat = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + tm * 8 + i;
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
     if (d.out_nchw) {
       int n = m / HoWo, rem = m - n * HoWo;
       for (int j = 0; j < 4 && nb + j < d.Cout; ++j)
-        store1f<FO>(out + ((size_t)n * d.Cout + nb + j) * HoWo + rem, d.out_plane_stride, v[j]);
+        store1f<FO>(out + ((size_t)n * d.Cout + nb + j) * HoWo + rem, d.out_plane_stride, v[j], sat);
     } else if (d.upsample2) {
       int n = m / HoWo, rem = m - n * HoWo;
       int oh = rem / d.Wo, ow = rem - oh * d.Wo;
@@ -343,15 +345,16 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
       for (int q = 0; q < 4; ++q) {
         size_t pix = ((size_t)n * 2 * d.Ho + 2 * oh + (q >> 1)) * W2 + 2 * ow + (q & 1);
         TOut* op = out + pix * d.out_cpitch + d.out_coff + nb;
-        if (vec_out) store4f<FO>(op, d.out_plane_stride, v);
-        else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1f<FO>(op + j, d.out_plane_stride, v[j]);
+        if (vec_out) store4f<FO>(op, d.out_plane_stride, v, sat);
+        else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1f<FO>(op + j, d.out_plane_stride, v[j], sat);
       }
     } else {
       TOut* op = out + (size_t)m * d.out_cpitch + d.out_coff + nb;
-      if (vec_out) store4f<FO>(op, d.out_plane_stride, v);
-      else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1f<FO>(op + j, d.out_plane_stride, v[j]);
+      if (vec_out) store4f<FO>(op, d.out_plane_stride, v, sat);
+      else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1f<FO>(op + j, d.out_plane_stride, v[j], sat);
     }
   }
+  if (sat && d.sat_flag) atomicOr(d.sat_flag, 1);
 }
 
 template <class FI, class FO>
@@ -444,6 +447,7 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
   const int sw_vpp = d.Cout / SW_E;                                // vectors per pixel row (power of two: Cout is 16 or 32)
   const int sw_rpl = max(1, 128 / (d.Cout * (int)sizeof(TOut)));   // pixel rows per 128-byte bank line
   const int sw_x = ((int)threadIdx.x / sw_rpl) & (sw_vpp - 1);
+  int sat = 0;
   for (int o0 = 0; o0 < d.Cout; o0 += STEM_CO) {
     float acc[STEM_CO];
 #pragma unroll
@@ -475,10 +479,11 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
         // 16-byte vectors of a pixel row are XOR-swizzled with the pixel index: a plain [pixel][Cout] staging buffer puts the
         // 32 threads of a store on 2-4 banks (row pitch 64/128 bytes), 16-way conflicts; un-swizzled again by the copy-out
         const int e = o0 + j4, vi = e / SW_E, within = e - vi * SW_E;
-        store4f<FO>(s_out + (size_t)threadIdx.x * d.Cout + ((vi ^ sw_x) * SW_E) + within, (long long)blockDim.x * d.Cout, v);
-      } else if (m < args.M) store4f<FO>(op + o0 + j4, d.out_plane_stride, v);
+        store4f<FO>(s_out + (size_t)threadIdx.x * d.Cout + ((vi ^ sw_x) * SW_E) + within, (long long)blockDim.x * d.Cout, v, sat);
+      } else if (m < args.M) store4f<FO>(op + o0 + j4, d.out_plane_stride, v, sat);
     }
   }
+  if (sat && d.sat_flag) atomicOr(d.sat_flag, 1);
   if (staged) {
     __syncthreads();
     const int rows = min((int)blockDim.x, args.M - m_blk0);
@@ -498,12 +503,9 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
 template <class FO>
 static void launch_stem_t(const ConvKArgs& a, int in_layout, int smem, cudaStream_t st) {
   const int blocks = (a.M + 255) / 256;
-  static bool attr_done = false;
-  if (!attr_done) {                                        // three staged 16-bit planes need more than the default 48 KB
-    cudaFuncSetAttribute(stem3x3_kernel<FO, IN_NCHW_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(stem3x3_kernel<FO, IN_NHWC_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_done = true;
-  }
+  // three staged 16-bit planes need more than the default 48 KB
+  ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_kernel<FO, IN_NCHW_F32>), 96 * 1024);
+  ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_kernel<FO, IN_NHWC_U8>), 96 * 1024);
   if (in_layout == IN_NCHW_F32) stem3x3_kernel<FO, IN_NCHW_F32><<<blocks, 256, smem, st>>>(a);
   else stem3x3_kernel<FO, IN_NHWC_U8><<<blocks, 256, smem, st>>>(a);
 }
@@ -539,6 +541,7 @@ __global__ void pool_kernel(const typename F::T* __restrict__ in, typename F::T*
                             int in_coff, long long in_ps, int out_cpitch, int out_coff, long long out_ps, int Ho, int Wo, int k,
                             int stride, int pad) {
   size_t total = (size_t)N * Ho * Wo * C;
+  int sat = 0;                                   // pooled values never exceed their (already representable) inputs
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     int c = (int)(idx % C);
     size_t pix = idx / C;
@@ -557,7 +560,7 @@ __global__ void pool_kernel(const typename F::T* __restrict__ in, typename F::T*
       }
     }
     if (!IS_MAX) acc = acc / (float)(k * k);     // gluon AvgPool2D: count_include_pad, no padding used here
-    store1f<F>(out + pix * out_cpitch + out_coff + c, out_ps, acc);
+    store1f<F>(out + pix * out_cpitch + out_coff + c, out_ps, acc, sat);
   }
 }
 

@@ -345,11 +345,8 @@ extern "C" int yolo_decode_nms(const yolo_decode_geom* g, const void* const* hea
     return fail(YOLO_E_BADARG, "decode_nms: need 1 <= max_out <= max_cand <= %d", kMaxCand);
   if (batch == 0) return YOLO_OK;
   NmsDev np{p->score_thr, p->iou_thr, p->max_out, p->max_cand};
-  static bool attr_set = false;
-  if (!attr_set) {
-    YB_CUDA(cudaFuncSetAttribute(decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem)));
-    attr_set = true;
-  }
+  rc = ensure_dyn_smem(reinterpret_cast<const void*>(&decode_kernel<1>), (int)sizeof(NmsSmem));
+  if (rc) return rc;
   dim3 grid(kCluster, batch);
   decode_kernel<1><<<grid, kThreads, sizeof(NmsSmem), (cudaStream_t)stream>>>(d, np, out_rows, out_idx, out_count);
   ++g_launches;

@@ -18,6 +18,8 @@
 
 #include <map>
 #include <memory>
+#include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -32,6 +34,18 @@ thread_local int g_launches = 0;
 std::string& tls_error() {
   static thread_local std::string e;
   return e;
+}
+
+int ensure_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  YB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({func, dev})) return YOLO_OK;
+  YB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({func, dev});
+  return YOLO_OK;
 }
 
 int fail(int code, const char* fmt, ...) {
@@ -328,6 +342,26 @@ static void* resolve(const yolo_handle* h, const View& v, const void* input, voi
   return outputs[-2 - v.buf];
 }
 
+// ConvDesc of one planned convolution for `batch` images (inference epilogue: folded BN, activation, residual, placement)
+void fill_conv_desc(const yolo_handle* h, const Op& op, int batch, const void* input, void* const* outputs, ConvDesc& d) {
+  memset(&d, 0, sizeof(d));
+  d.in = resolve(h, op.in, input, outputs);
+  d.in_dtype = op.in.dtype; d.N = batch; d.H = op.in.H; d.W = op.in.W; d.Cin = op.in.C;
+  d.in_cpitch = op.in.cpitch; d.in_coff = op.in.coff; d.in_plane_stride = op.in.ps;
+  d.kh = op.kh; d.kw = op.kw; d.stride = op.stride; d.pad = op.pad; d.Cout = op.cout;
+  d.w_f32 = op.w_f32; d.cout_pad = op.cout_pad;
+  d.pre_scale = op.pre_scale; d.pre_shift = op.pre_shift;
+  d.scale = op.scale; d.shift = op.shift; d.act = op.act;
+  if (op.has_res) { d.res = resolve(h, op.res, input, outputs); d.res_cpitch = op.res.cpitch; d.res_coff = op.res.coff; d.res_plane_stride = op.res.ps; }
+  d.out = resolve(h, op.out, input, outputs);
+  d.out_dtype = op.out.dtype;
+  d.Ho = (op.in.H + 2 * op.pad - op.kh) / op.stride + 1;
+  d.Wo = (op.in.W + 2 * op.pad - op.kw) / op.stride + 1;
+  d.out_cpitch = op.out.cpitch; d.out_coff = op.out.coff; d.out_plane_stride = op.out.ps;
+  d.upsample2 = op.upsample2; d.out_nchw = op.out_nchw;
+  d.sat_flag = h->d_flags;
+}
+
 }  // namespace yb
 
 // ------------------------------------------------------------------------------------------------
@@ -369,6 +403,7 @@ extern "C" int yolo_destroy(yolo_handle* h) {
   cudaSetDevice(h->device);
   if (h->dparams) cudaFree(h->dparams);
   if (h->stage) cudaFree(h->stage);
+  if (h->d_flags) cudaFree(h->d_flags);
   train_release(h);
   for (auto& op : h->ops) umma_release(op.umma);
   delete h;
@@ -439,6 +474,10 @@ extern "C" int yolo_finalize_params(yolo_handle* h, void* stream) {
   if (!h->dparams) {
     if (cudaMalloc(&h->dparams, total) != cudaSuccess) { cudaGetLastError(); return hfail(h, fail(YOLO_E_OOM, "finalize: cudaMalloc(%zu) failed", total)); }
     h->dparams_bytes = total;
+  }
+  if (!h->d_flags) {
+    YB_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_flags), 64));
+    YB_CUDA(cudaMemsetAsync(h->d_flags, 0, 64, st));
   }
   std::vector<float> stagev(total / 4, 0.f);
   char* dbase = static_cast<char*>(h->dparams);
@@ -566,21 +605,7 @@ extern "C" int yolo_forward(yolo_handle* h, const void* input, int batch, int in
                        op.is_max, st);
     } else {
       ConvDesc d;
-      memset(&d, 0, sizeof(d));
-      d.in = resolve(h, op.in, input, outputs);
-      d.in_dtype = op.in.dtype; d.N = batch; d.H = op.in.H; d.W = op.in.W; d.Cin = op.in.C;
-      d.in_cpitch = op.in.cpitch; d.in_coff = op.in.coff; d.in_plane_stride = op.in.ps;
-      d.kh = op.kh; d.kw = op.kw; d.stride = op.stride; d.pad = op.pad; d.Cout = op.cout;
-      d.w_f32 = op.w_f32; d.cout_pad = op.cout_pad;
-      d.pre_scale = op.pre_scale; d.pre_shift = op.pre_shift;
-      d.scale = op.scale; d.shift = op.shift; d.act = op.act;
-      if (op.has_res) { d.res = resolve(h, op.res, input, outputs); d.res_cpitch = op.res.cpitch; d.res_coff = op.res.coff; d.res_plane_stride = op.res.ps; }
-      d.out = resolve(h, op.out, input, outputs);
-      d.out_dtype = op.out.dtype;
-      d.Ho = (op.in.H + 2 * op.pad - op.kh) / op.stride + 1;
-      d.Wo = (op.in.W + 2 * op.pad - op.kw) / op.stride + 1;
-      d.out_cpitch = op.out.cpitch; d.out_coff = op.out.coff; d.out_plane_stride = op.out.ps;
-      d.upsample2 = op.upsample2; d.out_nchw = op.out_nchw;
+      fill_conv_desc(h, op, batch, input, outputs, d);
       const int lay = op.in.buf == -1 ? (in_layout == YOLO_IN_NCHW_F32 ? 1 : 2) : 0;
       if (op.umma.enabled) rc = launch_conv_umma(op.umma, d, st);
       else if (stem_eligible(d, lay)) rc = launch_stem(d, lay, st);
@@ -657,7 +682,6 @@ extern "C" int yolo_predict_host(yolo_handle* h, const void* host_input, int bat
   const size_t o_rows = take((size_t)C * 4 * s.max_batch), o_idx = take((size_t)4 * s.max_batch);
   if (!h->stage || h->stage_bytes < total) {
     if (h->stage) cudaFree(h->stage);
-  train_release(h);
     h->stage = nullptr;
     if (cudaMalloc(&h->stage, total) != cudaSuccess) { cudaGetLastError(); return hfail(h, fail(YOLO_E_OOM, "predict_host: cudaMalloc(%zu) failed", total)); }
     h->stage_bytes = total;
@@ -681,6 +705,20 @@ extern "C" int yolo_predict_host(yolo_handle* h, const void* host_input, int bat
   YB_CUDA(cudaMemcpyAsync(host_rows, sb + o_rows, (size_t)C * 4 * batch, cudaMemcpyDeviceToHost, st));
   if (host_idx) YB_CUDA(cudaMemcpyAsync(host_idx, sb + o_idx, (size_t)4 * batch, cudaMemcpyDeviceToHost, st));
   YB_CUDA(cudaStreamSynchronize(st));
+  return YOLO_OK;
+}
+
+extern "C" int yolo_check_saturation(yolo_handle* h, int32_t* flags_out, void* stream) {
+  if (!h || !flags_out) return fail(YOLO_E_BADARG, "check_saturation: null argument");
+  *flags_out = 0;
+  if (!h->d_flags) return YOLO_OK;
+  YB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int v = 0;
+  YB_CUDA(cudaMemcpyAsync(&v, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+  YB_CUDA(cudaMemsetAsync(h->d_flags, 0, sizeof(int), st));
+  YB_CUDA(cudaStreamSynchronize(st));
+  *flags_out = v;
   return YOLO_OK;
 }
 

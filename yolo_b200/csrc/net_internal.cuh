@@ -79,6 +79,7 @@ struct yolo_handle {
   // lazily allocated device staging for yolo_predict_host
   void* stage = nullptr;
   size_t stage_bytes = 0;
+  int* d_flags = nullptr;                  // device flags: [0] |= 1 activation left the fp16 range of the DT_F16X2 high plane, |= 2 weight did
   yb::TrainState* train = nullptr;         // training state (train_step.cu), null until yolo_train_init
 };
 
@@ -89,4 +90,5 @@ inline int hfail(yolo_handle* h, int code) {
   return code;
 }
 void train_release(yolo_handle* h);
+void fill_conv_desc(const yolo_handle* h, const Op& op, int batch, const void* input, void* const* outputs, ConvDesc& d);
 }  // namespace yb
