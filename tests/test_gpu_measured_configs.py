@@ -1,0 +1,172 @@
+"""GPU parity AT the configurations bench.py measures (BASELINE.json configs[1], [2], [4]) - full batch, max_batch = batch, default
+tile kinds, the bench's own synthetic weights - so plane strides, M tiles crossing 32 images and the CTA-pair kernels at 5-10 rounds
+are asserted, not only timed.  The fp32 oracle runs on every image (chunked), its fp64 evaluation on a few of them."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import check_top1_indices, cuda_net, noise_aware_check, oracle_outputs_chunked
+from oracle import decode, nets, weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _bench_params(net_obj, C):
+    from yolo_b200 import synth
+    return synth.random_params(net_obj.param_shapes(), seed=2024, channels_per_anchor=C)
+
+
+def test_cfg2_dk53_416_batch32():
+    """BASELINE configs[1]: Darknet-53 416x416, batch 32, fp16x3, the weights and frames of bench.py."""
+    import yolo_b200
+    B = 32
+    spec = dict(nets.spec_dk53(), classes=list(range(24)))
+    y = yolo_b200.YOLO(spec=spec, precision="fp16x3", max_batch=B)
+    params = _bench_params(y.net, 30)
+    y.net.load_params(params)
+    rng = np.random.default_rng(1234)
+    u8 = rng.integers(0, 256, size=(B, 416, 416, 3), dtype=np.uint8)
+    x = (u8.astype(np.float32).transpose(0, 3, 1, 2) / np.float32(255)).astype(np.float32)
+    out = y.net.forward(is_train=False, data=torch.from_numpy(u8).cuda())            # uint8 NHWC frames like the bench's e2e leg
+    pred, idx = y.predict(out, return_index=True)
+    heads = [o.asnumpy() for o in out]
+    assert y.net.saturated() == 0
+    ref32 = oracle_outputs_chunked("carnet", spec, params, x, chunk=8)
+    sub = [0, 17, 31]
+    ref64 = oracle_outputs_chunked("carnet", spec, params, x, torch.float64, chunk=1, images=sub)
+    noise = 0.0
+    for i in range(3):
+        _, nz = noise_aware_check(heads[i][sub], ref32[i][sub], ref64[i], what=f"cfg2 head{i}")
+        noise = max(noise, nz)
+        assert np.abs(heads[i] - ref32[i]).max() <= max(1e-4, 3 * noise) + 1e-4, f"cfg2 head{i} vs fp32 oracle (all 32 images)"
+    opred, oidx = decode.predict(spec, ref32, return_index=True)
+    check_top1_indices(idx, oidx, ref32, margin=max(2e-4, 4 * noise))
+    same = idx == oidx
+    assert same.sum() >= B - 1
+    assert np.abs(pred[same][:, :4] - opred[same][:, :4]).max() <= 1e-4              # score, y, x, h
+    assert np.abs(pred[same][:, 4] - opred[same][:, 4]).max() <= max(1e-4, 4 * noise)   # w = exp(tw) * anchor carries the logit error 1:1
+
+
+def test_cfg3_lpdensenet_batch64():
+    """BASELINE configs[2]: licence_plate v2 DenseNet 320x512, batch 64, pose-head decode for every image."""
+    import yolo_b200
+    B = 64
+    spec = nets.spec_lp_v2()
+    params = weights.make_params("lpdensenet", spec, seed=77, calib_batch=1)
+    x, u8 = weights.synthetic_frames(B, spec["size"], seed=99)
+    n = cuda_net("lpdensenet", spec, params, "fp16x3", max_batch=B)
+    out = n.forward(is_train=False, data=torch.from_numpy(x).cuda())
+    res = out[0].asnumpy()
+    ref32 = oracle_outputs_chunked("lpdensenet", spec, params, x, chunk=16)[0]
+    sub = [0, 63]
+    ref64 = oracle_outputs_chunked("lpdensenet", spec, params, x, torch.float64, chunk=2, images=sub)[0]
+    _, noise = noise_aware_check(res[sub], ref32[sub], ref64, what="cfg3 out")
+    assert np.abs(res - ref32).max() <= max(1e-4, 3 * noise) + 1e-4
+    rows, idx = yolo_b200.decode_lp(out[0], 1, spec["LP_r_max"])
+    rows, idx = rows.cpu().numpy(), idx.cpu().numpy()
+    for b in range(B):
+        orow, oi = decode.predict_LP_single(spec, ref32[b:b + 1], return_index=True)
+        if int(idx[b]) != oi:                                                         # raw-score argmax: accept fp32-resolution ties only
+            s = ref32[b, 0].reshape(-1)
+            assert s[oi] - s[int(idx[b])] <= max(2e-4, 4 * noise)
+            continue
+        np.testing.assert_allclose(rows[b], orow, rtol=0, atol=1e-4 * max(1.0, np.abs(orow).max()))
+
+
+def test_cfg5_car_and_lp_608_batch16():
+    """BASELINE configs[4]: car_and_LP Darknet-53 608x608 (CarLPNet, 106 convs), batch 16, three-scale decode + LP decode."""
+    import yolo_b200
+    B = 16
+    spec = dict(nets.spec_dk53((608, 608), 30, True), classes=list(range(24)))
+    params = weights.make_params("carlpnet", spec, seed=77, calib_batch=1)
+    x, _ = weights.synthetic_frames(B, spec["size"], seed=99)
+    y = yolo_b200.CarLPYOLO(spec=spec, params=params, precision="fp16x3", max_batch=B)
+    out = y.net.forward(is_train=False, data=torch.from_numpy(x).cuda())
+    res = [o.asnumpy() for o in out]
+    assert y.net.saturated() == 0
+    ref32 = oracle_outputs_chunked("carlpnet", spec, params, x, chunk=2)
+    sub = [0, 15]
+    ref64 = oracle_outputs_chunked("carlpnet", spec, params, x, torch.float64, chunk=1, images=sub)
+    noise = 0.0
+    for i in range(3):
+        _, nz = noise_aware_check(res[i][sub], ref32[i][sub].reshape(res[i][sub].shape), ref64[i].reshape(res[i][sub].shape), what=f"cfg5 head{i}")
+        noise = max(noise, nz)
+    _, lp_noise = noise_aware_check(res[3][sub], ref32[3][sub], ref64[3], floor=5e-4, what="cfg5 LP map")
+    pred, idx = y.predict(out, return_index=True)
+    opred, oidx = decode.predict(spec, ref32[:3], return_index=True)
+    check_top1_indices(idx, oidx, ref32[:3], margin=max(2e-4, 4 * noise))
+    same = idx == oidx
+    assert np.abs(pred[same][:, :4] - opred[same][:, :4]).max() <= 1e-4
+    lrows, lidx = y.predict_LP([out[3]], return_index=True)
+    olr, oli = decode.predict_LP_batch(spec, ref32[3], return_index=True)
+    lsame = lidx == oli
+    assert lsame.sum() >= B - 1
+    assert np.abs(lrows[lsame][:, 0] - olr[lsame][:, 0]).max() <= 5e-4               # LP branch: 31 chained convs
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1e-1, 1e1, 1e3])
+def test_fp16x3_activation_scale_sweep(scale):
+    """fp16x3 stores activations as hi + lo fp16 planes with an UNSCALED low plane: an absolute-error format.  Sweep the activation
+    magnitude of a conv layer pair over six decades (input conv's BN gamma/beta scaled): relative error of the second conv's
+    output must stay fp32-grade where the format is specified (|v| in ~[1e-2, 6e4]) and degrade gracefully below."""
+    import yolo_b200
+    spec = {"size": [40, 40], "cin": 64, "cout": 128, "k": 3, "stride": 1, "pad": 1, "act": 1, "residual": 0, "bn": 1}
+    rng = np.random.default_rng(3)
+    n = yolo_b200.Net("debugconv", spec, precision="fp16x3", max_batch=2)
+    p = {}
+    for name, shape in n.param_shapes():
+        leaf = name.rsplit(".", 1)[1]
+        if leaf == "weight":
+            fan = shape[1] * shape[2] * shape[3]
+            p[name] = (rng.standard_normal(shape) / np.sqrt(fan)).astype(np.float32)
+        elif leaf == "gamma":
+            p[name] = np.full(shape, scale if name.startswith("pre") else 1.0 / scale, np.float32)     # second BN brings the result back to O(1)
+        elif leaf == "beta":
+            p[name] = (rng.standard_normal(shape) * (0.1 * scale if name.startswith("pre") else 0.1)).astype(np.float32)
+        elif leaf == "running_mean":
+            p[name] = np.zeros(shape, np.float32)
+        elif leaf == "running_var":
+            p[name] = np.ones(shape, np.float32)
+        else:
+            p[name] = np.zeros(shape, np.float32)
+    n.load_params(p)
+    x = rng.uniform(0, 1, size=(2, 3, 40, 40)).astype(np.float32)
+    got = n.forward(data=torch.from_numpy(x).cuda())[0].asnumpy()                     # (B, H, W, Cout) fp32
+    assert n.saturated() == 0
+    import torch.nn.functional as F
+    t = lambda a: torch.from_numpy(np.asarray(a)).double()
+    def bn(z, pre):
+        g, b = t(p[pre + ".gamma"]), t(p[pre + ".beta"])
+        return z * (g / torch.sqrt(torch.ones_like(g) + 1e-5)).view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+    a = F.leaky_relu(bn(F.conv2d(t(x), t(p["pre.weight"]), padding=1), "pre"), 0.1)
+    ref = F.leaky_relu(bn(F.conv2d(a, t(p["test.weight"]), padding=1), "test"), 0.1).permute(0, 2, 3, 1).numpy()
+    rel = np.abs(got - ref).max() / np.abs(ref).max()
+    # |v| >= ~0.1: 22-bit operands, fp32-grade.  Below, the unscaled low plane becomes subnormal (absolute spacing 6e-8): the relative
+    # error grows like 3e-8 / |v| - graceful, documented in DESIGN.md section 4 (BatchNorm keeps real activations at O(1)).
+    tol = {1e-3: 3e-4, 1e-1: 5e-6}.get(scale, 2e-6)
+    assert rel <= tol, (scale, rel)
+    print(f"fp16x3 activation scale {scale:g}: max rel err {rel:.2e}")
+
+
+def test_fp16x3_saturation_is_flagged():
+    """Activations beyond the fp16 range of the high plane (65504) are clamped - and the handle says so."""
+    import yolo_b200
+    spec = {"size": [32, 32], "cin": 64, "cout": 64, "k": 1, "stride": 1, "pad": 0, "act": 1, "residual": 2, "bn": 1}
+    rng = np.random.default_rng(4)
+    for gamma, expect in ((1.0, 0), (3e5, 1)):
+        n = yolo_b200.Net("debugconv", spec, precision="fp16x3", max_batch=1)
+        p = {}
+        for name, shape in n.param_shapes():
+            leaf = name.rsplit(".", 1)[1]
+            if leaf == "weight":
+                p[name] = (rng.standard_normal(shape) / np.sqrt(shape[1] * shape[2] * shape[3])).astype(np.float32)
+            elif leaf == "gamma":
+                p[name] = np.full(shape, gamma if name.startswith("test") else 1.0, np.float32)
+            elif leaf == "running_var":
+                p[name] = np.ones(shape, np.float32)
+            else:
+                p[name] = np.zeros(shape, np.float32)
+        n.load_params(p)
+        n.forward(data=torch.from_numpy(rng.uniform(0, 1, size=(1, 3, 32, 32)).astype(np.float32)).cuda())
+        assert (n.saturated() & 1) == expect, (gamma, expect)
+        assert n.saturated() == 0                      # reading clears
