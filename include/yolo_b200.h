@@ -155,6 +155,12 @@ int  yolo_check_saturation(yolo_handle* h, int32_t* flags_out, void* stream);
 /* Debug/parity: copy an internal activation (by oracle layer name) to host as NCHW fp32. */
 int  yolo_debug_activation(yolo_handle* h, const char* layer_name, int batch, float* host_nchw, size_t n_elems);
 
+/* Debug/parity: weight gradient of ONE convolution through the tcgen05 weight-gradient kernel of the training step.
+ * x: device fp32 NHWC (n,h,w,cin); dz: device fp32 (n*ho*wo, cout); dW: device fp32 [k*k*cin][cout], row = (r*k+s)*cin + c.
+ * cin % 64 == 0 and cout % 64 == 0.  variant = 0 (other values probe descriptor conventions in the unit test). */
+int  yolo_debug_wgrad(const float* x, const float* dz, int n, int h, int w, int cin, int cout, int k, int stride, int pad,
+                      float* dW, int variant, void* stream);
+
 /* Decode + selection (fused, one launch).  heads: device fp32, shallow -> deep.
  * out_rows (B, C) fp32 = [sigmoid(score), y, x, h, w, rotate, class logits...]; out_idx (B) int32 flat index. */
 int  yolo_decode_top1(const yolo_decode_geom* g, const void* const* heads, int batch,

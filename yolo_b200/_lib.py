@@ -68,6 +68,7 @@ SYMBOLS = {
     "yolo_forward": (_I, [_VP, _VP, _I, _I, C.POINTER(_VP), _VP]),
     "yolo_check_saturation": (_I, [_VP, C.POINTER(C.c_int32), _VP]),
     "yolo_debug_activation": (_I, [_VP, C.c_char_p, _I, _VP, _SZ]),
+    "yolo_debug_wgrad": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _VP, _I, _VP]),
     "yolo_decode_top1": (_I, [C.POINTER(DecodeGeom), C.POINTER(_VP), _I, _VP, _VP, _VP]),
     "yolo_decode_nms": (_I, [C.POINTER(DecodeGeom), C.POINTER(_VP), _I, C.POINTER(NmsParams), _VP, _VP, _VP, _VP]),
     "yolo_decode_lp": (_I, [_VP, _I, _I, _I, _I, _I, C.POINTER(C.c_float * 3), _VP, _VP, _VP]),
