@@ -155,40 +155,62 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def train_probe(spec, local, batch=16, steps=3):
-    """Secondary measurement (BASELINE configs[3] per-GPU batch): one data-parallel training step = train-mode forward, targets +
-    losses, backward, Adam (fp32 FFMA kernels), timed with CUDA events.  Never fails the bench: errors are reported as text."""
+def train_probe(spec, local, world, pk, batch=16, steps=5):
+    """BASELINE configs[3] (car/YOLO.py training step, Darknet-53 416x416, 16 images per GPU = batch 128 on 8 GPUs): train-mode forward,
+    targets + losses, backward, gradient all-reduce over the ranks (NCCL, bucketed, overlapped with the backward - INSIDE the timed
+    region), Adam.  fp32-grade arithmetic on tcgen05 (fp16x3).  Timed with CUDA events, max over ranks.  Every rank must call this.
+    Never fails the bench: errors are reported as text."""
     try:
         import numpy as np
         import torch
+        import torch.distributed as dist
 
         import yolo_b200
         from yolo_b200 import synth
         tspec = dict(spec, batch_size=batch, learning_rate=0.001, scale={"score": 0.1, "box_yx": 0.01, "box_hw": 10.0, "rotate": 0.0, "class": 0.3},
                      positive_weight=1.0, negative_weight=0.1)
-        y = yolo_b200.YOLO(spec=tspec, precision="fp32", max_batch=batch, gpu=local)
-        y.net.load_params(synth.random_params(y.net.param_shapes(), seed=1, channels_per_anchor=30))
+        dev = torch.device("cuda", local)
+        y = yolo_b200.YOLO(spec=tspec, precision="fp16x3", max_batch=batch, gpu=local)
         S = spec["size"][0]
-        x = torch.rand((batch, 3, S, S), device=f"cuda:{local}")
+        rank = int(os.environ.get("RANK", "0"))
+        x = torch.rand((batch, 3, S, S), device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank))
+        synth.calibrated_params(y.net, x[:4].contiguous(), seed=1, channels_per_anchor=30)
         lab = np.full((batch, 1, 30), -1.0, np.float32)
         lab[:, 0, :6] = [3, .5, .5, .3, .3, 0]
         lab[:, 0, 6:] = 1.0 / 24
-        y._train_batch([x], [lab])
+        for _ in range(2):
+            y._train_batch([x], [lab])
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             y._train_batch([x], [lab])
         e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-        out = {"images_per_s": batch / (ms / 1e3), "ms_per_step": ms, "batch_per_gpu": batch, "dtype": "f32 (FFMA kernels)",
-               "tflops": 3 * y.net.conv_flops_per_image * batch / (ms / 1e3) / 1e12, "launches_per_step": y.net.launches + 1,
-               "what": "train-mode forward + targets/losses + backward + Adam (car/YOLO.py:350-399), no all-reduce at N=1"}
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        flops = 3 * y.net.conv_flops_per_image * batch
+        peak_tf = float(pk.get("bf16_tflops_sustained", 1400.0)) / 3
+        ach = flops / (ms / 1e3) / 1e12
+        sat = y.net.saturated()
+        out = {"images_per_s": world * batch / (ms / 1e3), "ms_per_step": ms, "batch_per_gpu": batch, "global_batch": world * batch, "n_gpus": world,
+               "dtype": "f32 (emulated: 3 fp16 tcgen05 passes, fp32 accumulate) forward, dgrad and wgrad",
+               "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                            "algorithmic_flops_per_step_per_gpu": flops, "note": "3 x forward conv FLOPs (forward + dgrad + wgrad) per GPU"},
+               "launches_per_step": y.net.launches, "fp16_saturation_flags": sat,
+               "allreduce": (f"ncclAllReduce(sum, fp32) of {y.trainer.G.numel() * 4 / 1e6:.1f} MB in 64 MB buckets issued from the backward as each "
+                             f"bucket completes (library communicator joined: {y.trainer.nccl_joined})") if world > 1 else "none at N=1",
+               "what": "train-mode forward + targets/losses + backward + gradient all-reduce + Adam (car/YOLO.py:350-399)"}
         del y
         torch.cuda.empty_cache()
         return out
     except Exception as e:          # noqa: BLE001
-        return {"error": repr(e)[:300]}
+        import traceback
+        return {"error": repr(e)[:300], "trace": traceback.format_exc()[-600:]}
 
 
 DK53_ANCHORS = [[[0.2216, 0.1552], [0.2144, 0.2408], [0.2825, 0.3456]], [[0.3959, 0.2706], [0.3703, 0.4351], [0.5708, 0.4278]],
@@ -369,12 +391,17 @@ def run_ours(args):
     spec = dk53_spec(S)
     y = yolo_b200.YOLO(args=None, spec=spec, precision=precision, max_batch=B, gpu=local)
     # every rank = an independent replica with the same weights (inference shards by batch, no collective)
-    params = synth.random_params(y.net.param_shapes(), seed=2024, channels_per_anchor=30)
-    y.net.load_params(params)
     rng = np.random.default_rng(1234 + rank)
     frames_u8 = torch.from_numpy(rng.integers(0, 256, size=(B, S, S, 3), dtype=np.uint8))
     host_frames = frames_u8.pin_memory()
     x_dev = (frames_u8.to(dev).permute(0, 3, 1, 2).float() / 255.0).contiguous()      # cv_img_2_ndarray layout, resident in HBM
+    # random-init weights (no checkpoints offline) with BatchNorm running statistics calibrated on 4 frames by one train-mode forward
+    # on this GPU, so that activations and head logits are O(1) like a trained net's
+    if precision == "fp16x3":
+        params = synth.calibrated_params(y.net, x_dev[:min(4, B)].contiguous(), seed=2024, channels_per_anchor=30)
+    else:
+        params = synth.random_params(y.net.param_shapes(), seed=2024, channels_per_anchor=30)
+        y.net.load_params(params)
 
     stream = torch.cuda.current_stream(dev)
     def barrier():
@@ -442,9 +469,14 @@ def run_ours(args):
         p_rows, p_idx = y.predict(o, return_index=True)
         parity = parity_block(spec, params, frames_u8.numpy(), [t.asnumpy() for t in o], p_rows, p_idx)
 
+    flops_img = y.net.conv_flops_per_image
+    train = None
+    if not args.no_train:
+        y = None                                  # free the inference replica before the training arena is allocated
+        torch.cuda.empty_cache()
+        train = train_probe(spec, local, world, peaks()[0])
     if rank == 0:
         pk, pk_src = peaks()
-        flops_img = y.net.conv_flops_per_image
         passes = {"fp16x3": 3, "bf16x6": 6, "bf16": 1, "fp32": 1}[precision]
         if precision == "fp32":
             peak_tf, peak_note = 72.0, "fp32 FFMA nominal (148 SM x 128 lanes x 2 x ~1.9 GHz); not a tensor-core kernel"
@@ -480,17 +512,15 @@ def run_ours(args):
                                 "unit": "GB/s", "frac": dec_bytes / (dec_ms / 1e3) / 1e9 / float(pk.get("hbm_gbs", 6650.0)),
                                 "algorithmic_bytes_per_step": dec_bytes, "avg_decode_ms": dec_ms, "peak_source": pk_src,
                                 "note": "heads were just written by the head convs (L2-resident); launch-latency bound at this size"},
-            "parity": parity, "fp16_saturation_flags": saturated,
+            "parity": parity, "fp16_saturation_flags": saturated, "train_step": train,
             "clocks": clocks, "wall_s": wall,
             "step_ms_each": [round(ev[3 * i].elapsed_time(ev[3 * i + 3]), 3) for i in range(args.steps)],
         }
         if world == 1 and not args.no_secondary:
-            del y
             y = None
             torch.cuda.empty_cache()
             line["other_configs"] = secondary_configs(local, pk)
-        if world == 1 and not args.no_train:
-            line["train_step"] = train_probe(spec, local)
+
         if world == 1 and not args.no_cpu_baseline:
             y = None
             torch.cuda.empty_cache()

@@ -28,6 +28,8 @@
  *   yolo_train_init / yolo_train_forward_backward / yolo_train_apply
  *                                   <- _init_train + _train_batch + gluon.Trainer.step(batch_size) with Adam
  *                                      car/YOLO.py:157-207,350-399
+ *   yolo_nccl_unique_id / yolo_train_comm_init
+ *                                   <- kvstore 'device' gradient reduction inside trainer.step  car/YOLO.py:396
  *   yolo_get_param                  <- net.collect_params().save(...)  car/YOLO.py:546-549 (read-back for checkpoints)
  *   yolo_predict_host               <- cv_img_2_ndarray + net.forward + predict + asnumpy
  *                                      yolo_modules/yolo_gluon.py:335-357, car/YOLO.py:597
@@ -185,14 +187,25 @@ int  yolo_loss_targets(const yolo_decode_geom* g, const void* const* heads, cons
                        const yolo_loss_params* p, void* scratch, float* out_losses, void* const* dheads, int32_t* out_assign,
                        void* stream);
 
-/* Training step (fp32, CARNET), one process per GPU.  The four flat buffers (parameters, gradients, Adam m, Adam v) are
- * caller-owned device memory of yolo_train_flat_size() floats each, so the data-parallel gradient exchange is ONE
- * all-reduce(sum) over `grads_flat` between forward_backward and apply (the reference sums over contexts inside
- * trainer.step through kvstore 'device', car/YOLO.py:396).  BatchNorm statistics stay local to the GPU (car/YOLO.py:94-96).
- *   forward_backward: train-mode forward, targets + the five losses -> out_losses (device, (5,B)), backward of their sum.
- *   apply: w -= lr_t * m / (sqrt(v) + eps) with g = grads * rescale_grad (= 1/global batch), lr_t = lr*sqrt(1-b2^t)/(1-b1^t). */
+/* Training step (CARNET / CARLPNET, YOLO_PREC_FP16X3 = fp32-grade arithmetic on the tensor cores), one process per GPU.  The four
+ * flat buffers (parameters, gradients, Adam m, Adam v) are caller-owned device memory of yolo_train_flat_size() floats each.
+ * BatchNorm statistics stay local to the GPU (car/YOLO.py:94-96).  Every reduction is fixed-order: a step is bit-reproducible.
+ *   forward_backward: train-mode forward, targets + the five losses -> out_losses (device, (5,B)), backward of their sum.  With a
+ *                     communicator attached (yolo_train_comm_init) the gradient is summed over ranks bucket by bucket WHILE the
+ *                     backward runs (ncclAllReduce on a side stream as each bucket's weight gradients complete); the call's stream
+ *                     waits for the last bucket.  The reference sums over contexts in trainer.step via kvstore 'device' (car/YOLO.py:396).
+ *                     NCCL failures return YOLO_E_NCCL.  Without a communicator the caller may all-reduce `grads_flat` itself.
+ *   apply: w -= lr_t * m / (sqrt(v) + eps) with g = grads * rescale_grad (= 1/global batch), lr_t = lr*sqrt(1-b2^t)/(1-b1^t); then the
+ *          fp16 weight planes are re-packed on the device and the inference epilogues refolded (yolo_forward serves the trained net).
+ *   set_bn_momentum: running = momentum*running + (1-momentum)*batch statistic; default 0.9 (gluon).  0 makes one forward a
+ *          calibration pass (synthetic weights).
+ *   nccl_unique_id / train_comm_init: rank 0 creates a 128-byte NCCL id, every rank receives it (any transport) and joins.
+ *          bucket_bytes = all-reduce granularity (0: 64 MB). */
 size_t yolo_train_flat_size(const yolo_handle* h);
 int  yolo_train_init(yolo_handle* h, float* params_flat, float* grads_flat, float* adam_m, float* adam_v, size_t n_flat, void* stream);
+int  yolo_train_set_bn_momentum(yolo_handle* h, float momentum);
+int  yolo_nccl_unique_id(void* id128);
+int  yolo_train_comm_init(yolo_handle* h, const void* id128, int rank, int world, size_t bucket_bytes);
 int  yolo_train_forward_backward(yolo_handle* h, const void* input, int in_layout, const float* labels, int batch, int n_obj,
                                  const yolo_loss_params* lp, float* out_losses, void* stream);
 int  yolo_train_apply(yolo_handle* h, float lr, float beta1, float beta2, float eps, float rescale_grad, void* stream);

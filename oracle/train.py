@@ -189,7 +189,7 @@ TRAINABLE = ("weight", "gamma", "beta", "bias")
 
 
 def train_step(net, spec, params, x, labels, hp, lr=0.001, batch_size=None, adam=None, t=1, car_rotate=False,
-               beta1=0.9, beta2=0.999, eps=1e-8):
+               beta1=0.9, beta2=0.999, eps=1e-8, dtype=torch.float32):
     """Forward in train mode (batch-statistics BN, per device), targets, the five losses, ``sum(losses).backward()``,
     then ``trainer.step(batch_size)``: grad * (1/batch_size) -> MXNet ``adam_update`` with the bias-corrected lr
     (``lr * sqrt(1-beta2^t)/(1-beta1^t)``, epsilon outside the square root, wd 0).  Single device (the multi-context sum of
@@ -197,8 +197,8 @@ def train_step(net, spec, params, x, labels, hp, lr=0.001, batch_size=None, adam
     from . import nets
     import math
     batch_size = batch_size or x.shape[0]
-    tp = {k: torch.tensor(np.asarray(v), dtype=torch.float32, requires_grad=k.rsplit(".", 1)[1] in TRAINABLE) for k, v in params.items()}
-    out, new_stats = nets.forward(net, spec, tp, torch.as_tensor(x), train=True)
+    tp = {k: torch.tensor(np.asarray(v), dtype=dtype, requires_grad=k.rsplit(".", 1)[1] in TRAINABLE) for k, v in params.items()}
+    out, new_stats = nets.forward(net, spec, tp, torch.as_tensor(x).to(dtype), train=True)          # dtype=float64: the noise reference of the parity tests
     heads = out if net == "carnet" else out[0]
     targets, mask, assign = loss_mask(spec, labels)
     losses = get_loss(spec, heads, targets, mask, hp, car_rotate)

@@ -11,9 +11,10 @@ from oracle import decode, nets, weights
 pytestmark = pytest.mark.gpu
 
 
-def _bench_params(net_obj, C):
+def _bench_params(net_obj, C, calib_frames):
+    """bench.py's weights: random init, BatchNorm running statistics calibrated by one train-mode forward on the GPU."""
     from yolo_b200 import synth
-    return synth.random_params(net_obj.param_shapes(), seed=2024, channels_per_anchor=C)
+    return synth.calibrated_params(net_obj, calib_frames, seed=2024, channels_per_anchor=C)
 
 
 def test_cfg2_dk53_416_batch32():
@@ -22,11 +23,10 @@ def test_cfg2_dk53_416_batch32():
     B = 32
     spec = dict(nets.spec_dk53(), classes=list(range(24)))
     y = yolo_b200.YOLO(spec=spec, precision="fp16x3", max_batch=B)
-    params = _bench_params(y.net, 30)
-    y.net.load_params(params)
     rng = np.random.default_rng(1234)
     u8 = rng.integers(0, 256, size=(B, 416, 416, 3), dtype=np.uint8)
     x = (u8.astype(np.float32).transpose(0, 3, 1, 2) / np.float32(255)).astype(np.float32)
+    params = _bench_params(y.net, 30, torch.from_numpy(x[:4]).cuda())
     out = y.net.forward(is_train=False, data=torch.from_numpy(u8).cuda())            # uint8 NHWC frames like the bench's e2e leg
     pred, idx = y.predict(out, return_index=True)
     heads = [o.asnumpy() for o in out]

@@ -79,83 +79,137 @@ def _train_case(spec, B, nobj, seed):
     return params, x, labels
 
 
-@pytest.mark.parametrize("spec,B", [(nets.spec_tiny(size=(64, 96), C=10), 2), (nets.spec_micro(size=(128, 128), C=8), 3)])
+def spec_mid(size=(64, 64), C=10):
+    """Channels the tensor-core kernels take (multiples of 32 / 64): forward, data-gradient and weight-gradient all run on tcgen05."""
+    return dict(size=list(size), layers=[1, 2, 1], channels=[32, 64, 128, 256], slice_point=[1, 3, 5, 6, C], all_anchors=nets.V1_ANCHORS,
+                use_fp16=False)
+
+
+def _grad_check(tr, shapes, ref32, ref64, floor=1e-3, names=None):
+    """Relative L2 error of every gradient against the fp64 oracle <= max(floor, 2 x the fp32 oracle's own error)."""
+    worst = (0.0, "")
+    for name in (names or ref32["grads"].keys()):
+        g64 = ref64["grads"][name]
+        got = tr.get_param(name, shapes[name], grad=True).astype(np.float64)
+        nrm = max(np.linalg.norm(g64), 1e-30)
+        rel = np.linalg.norm(got - g64) / nrm
+        noise = np.linalg.norm(ref32["grads"][name].astype(np.float64) - g64) / nrm
+        assert rel <= max(floor, 2 * noise), f"{name}: gradient rel L2 error {rel:.2e} (fp32 oracle's own {noise:.2e}, |g| {nrm:.2e})"
+        worst = max(worst, (rel, name))
+    return worst
+
+
+@pytest.mark.parametrize("spec,B", [(nets.spec_tiny(size=(64, 96), C=10), 2), (spec_mid(), 3), (spec_mid((96, 64), 12), 2)])
 def test_train_step_matches_oracle(spec, B):
-    """One full step (train-mode forward, losses, backward, Adam) against torch autograd + the restated MXNet Adam."""
+    """One full step (train-mode forward, losses, backward, Adam) against torch autograd + the restated MXNet Adam.
+    spec_tiny exercises the FFMA fallbacks (channels < 32), spec_mid the tcgen05 forward / dgrad / wgrad kernels."""
     import yolo_b200
     params, x, labels = _train_case(spec, B, 2, 31)
     hp = train.V1_HPARAMS
     ref = train.train_step("carnet", spec, params, x, labels, hp, lr=0.001, batch_size=B)
-    net = yolo_b200.Net("carnet", spec, precision="fp32", max_batch=B)
+    ref64 = train.train_step("carnet", spec, params, x, labels, hp, lr=0.001, batch_size=B, dtype=torch.float64)
+    net = yolo_b200.Net("carnet", spec, precision="fp16x3", max_batch=B)
     net.load_params(params)
     tr = yolo_b200.Trainer(net, learning_rate=0.001)
-    losses = tr.forward_backward(torch.from_numpy(x).cuda(), labels, hp["scale"], hp["positive_weight"], hp["negative_weight"])
+    xs = torch.from_numpy(x).cuda()
+    losses = tr.forward_backward(xs, labels, hp["scale"], hp["positive_weight"], hp["negative_weight"])
     np.testing.assert_allclose(losses.cpu().numpy(), ref["losses"], rtol=2e-4, atol=1e-8)
     shapes = dict(net.param_shapes())
-    worst = 0.0
-    for name, g in ref["grads"].items():
-        got = tr.get_param(name, shapes[name], grad=True)
-        scale = max(np.abs(g).max(), 1e-6)
-        err = np.abs(got - g).max() / scale
-        worst = max(worst, err)
-        assert err < 2e-2, f"{name}: grad rel err {err:.2e} (|g|max {scale:.2e})"   # fp32 backward through ~40 layers, atomics in wgrad
+    worst = _grad_check(tr, shapes, ref, ref64)
+    print(f"worst gradient rel L2 error {worst[0]:.2e} ({worst[1]})")
+    g1 = tr.G.clone()
+    tr.forward_backward(xs, labels, hp["scale"], hp["positive_weight"], hp["negative_weight"])
+    # running statistics moved, but the gradient does not depend on them: the step is bit-reproducible (no floating-point atomics)
+    assert torch.equal(g1, tr.G)
+    assert net.saturated() == 0
     tr.step(B)
     # Adam's first step moves every weight by ~lr*sign(g): where |g| is comparable to epsilon (1e-8) a 1e-10 difference in
     # the gradient changes the update, so a handful of near-zero-gradient elements may differ by up to 2*lr.
     n_bad = n_all = 0
     for name, v in ref["params"].items():
+        if name.endswith(("running_mean", "running_var")):
+            continue                                    # two forwards ran: checked separately below
         got = tr.get_param(name, shapes[name])
-        tol = 2e-5 + 2e-3 * np.abs(v).max() * name.endswith("running_var")
         diff = np.abs(got - v)
-        assert diff.max() <= 2.1e-3 + tol, f"{name}: {diff.max():.2e}"
-        n_bad += int((diff > tol).sum()); n_all += diff.size
+        assert diff.max() <= 2.1e-3 + 2e-5, f"{name}: {diff.max():.2e}"
+        n_bad += int((diff > 2e-5).sum()); n_all += diff.size
     assert n_bad <= 2e-3 * n_all, f"{n_bad} of {n_all} parameters differ after the Adam step"
     # the inference path now runs on the trained weights / refolded BN: compare it with the oracle evaluated on the
     # parameters READ BACK from the GPU (the oracle's own updated parameters differ in the few Adam sign-flip elements)
     back = {name: torch.from_numpy(tr.get_param(name, shp)) for name, shp in net.param_shapes()}
-    heads = net.forward(data=torch.from_numpy(x).cuda())
+    heads = net.forward(data=xs)
     with torch.no_grad():
         oh = nets.forward("carnet", spec, back, torch.from_numpy(x))
     for a, b in zip(heads, oh):
         np.testing.assert_allclose(a.asnumpy(), b.numpy(), rtol=0, atol=1e-3 * max(1.0, float(b.abs().max())))
 
 
+def test_running_statistics_and_trainer_lifetime():
+    """BatchNorm running statistics after ONE forward match the oracle; predict_host between steps leaves the training state alone
+    (round-1 bug: it released it); dropping the Trainer keeps the net serving the trained weights."""
+    import gc
+    import yolo_b200
+    spec = dict(spec_mid(), classes=[0, 1, 2, 3], batch_size=3, learning_rate=0.001, **train.V1_HPARAMS)
+    params, x, labels = _train_case(spec, 3, 1, 11)
+    ref = train.train_step("carnet", spec, params, x, labels, train.V1_HPARAMS, batch_size=3)
+    y = yolo_b200.YOLO(spec=spec, params=params, precision="fp16x3", max_batch=3)
+    xs = torch.from_numpy(x).cuda()
+    y._train_batch([xs], [labels])
+    shapes = dict(y.net.param_shapes())
+    for name, v in ref["params"].items():
+        if name.endswith(("running_mean", "running_var")):
+            np.testing.assert_allclose(y.trainer.get_param(name, shapes[name]), v, rtol=2e-4, atol=2e-6, err_msg=name)
+    rows, idx = y.net.predict_host(torch.from_numpy(x).pin_memory())          # validation between steps
+    y._train_batch([xs], [labels])                                            # the training state is still there
+    assert y.backward_counter == 2
+    w_trained = y.trainer.get_param("stages.1.0.weight", shapes["stages.1.0.weight"])
+    heads_before = [o.asnumpy() for o in y.net.forward(data=xs)]
+    net = y.net
+    del y.trainer, y
+    net._trainer = None
+    gc.collect(); torch.cuda.empty_cache()
+    net.load_params({n: (params[n] if not n.endswith("stages.1.0.weight") else w_trained) for n in params})   # finalize releases the stale trainer
+    assert net.forward(data=xs)[0].shape == heads_before[0].shape
+
+
 def test_train_batch_driver_surface_and_loss_goes_down():
     import yolo_b200
-    spec = dict(nets.spec_micro(size=(128, 128), C=8), classes=[0, 1], batch_size=4, learning_rate=0.001, **train.V1_HPARAMS)
+    spec = dict(nets.spec_tiny(size=(128, 128), C=8), classes=[0, 1], batch_size=4, learning_rate=0.001, **train.V1_HPARAMS)
     params, x, labels = _train_case(spec, 4, 1, 7)
-    y = yolo_b200.YOLO(spec=spec, params=params, precision="fp32", max_batch=4)
+    y = yolo_b200.YOLO(spec=spec, params=params, precision="fp16x3", max_batch=4)
     xs = torch.from_numpy(x).cuda()
     first = None
     for it in range(8):
-        assert y._train_batch([xs], [labels]) is None
+        assert y.train_step([xs], [labels]) is None
         tot = float(y.last_losses.sum())
         first = tot if first is None else first
     assert y.backward_counter == 8 and tot < first
+    with pytest.raises(ValueError):
+        y._train_batch([xs, xs], [labels, labels])       # torchrun contract: one list entry per process
 
 
 def test_train_step_dk53_416():
-    """BASELINE config 4 network (Darknet-53 416x416), one step at batch 2: losses and the head-side gradients against the
-    oracle (the deep-layer gradients of a 75-conv fp32 backward are compared on their norm)."""
+    """BASELINE config 4 network (Darknet-53 416x416), one step at batch 2: losses and gradients from the heads down to the stem
+    against the oracle, noise-aware (fp64 oracle as the truth, the fp32 oracle's own error as the resolution)."""
     import yolo_b200
     spec = nets.spec_dk53()
     B = 2
-    params, x, labels = _train_case(spec, B, 1, 5)
-    labels[:, 0, 0] = np.abs(labels[:, 0, 0])                 # make sure every image has an object
+    params, x, _ = _train_case(spec, B, 1, 5)
     labels = train.synthetic_labels(B, 24, nobj=1, seed=3, p_box=1.0)
     hp = train.V1_HPARAMS
     ref = train.train_step("carnet", spec, params, x, labels, hp, batch_size=B)
-    net = yolo_b200.Net("carnet", spec, precision="fp32", max_batch=B)
+    ref64 = train.train_step("carnet", spec, params, x, labels, hp, batch_size=B, dtype=torch.float64)
+    net = yolo_b200.Net("carnet", spec, precision="fp16x3", max_batch=B)
     net.load_params(params)
     tr = yolo_b200.Trainer(net)
     losses = tr.forward_backward(torch.from_numpy(x).cuda(), labels, hp["scale"], hp["positive_weight"], hp["negative_weight"])
     np.testing.assert_allclose(losses.cpu().numpy(), ref["losses"], rtol=1e-3, atol=1e-8)
     shapes = dict(net.param_shapes())
-    for name in ("yolo_outputs.0.weight", "yolo_outputs.2.bias", "yolo_blocks.2.tip.weight", "yolo_blocks.0.body.1.gamma", "stages.5.4.body.1.weight",
-                 "stages.3.1.body.0.weight", "stages.1.0.weight", "stages.0.weight", "stages.0.beta"):
-        g = ref["grads"][name]
-        got = tr.get_param(name, shapes[name], grad=True)
-        rel = np.linalg.norm(got - g) / max(np.linalg.norm(g), 1e-12)
-        assert rel < 2e-2, f"{name}: relative L2 error of the gradient {rel:.2e}"
+    names = ("yolo_outputs.0.weight", "yolo_outputs.2.bias", "yolo_blocks.2.tip.weight", "yolo_blocks.0.body.1.gamma", "stages.5.4.body.1.weight",
+             "stages.4.0.weight", "stages.3.1.body.0.weight", "stages.2.0.weight", "stages.1.1.body.0.weight", "stages.1.0.weight", "stages.0.weight",
+             "stages.0.beta", "transitions.0.weight")
+    worst = _grad_check(tr, shapes, ref, ref64, floor=1e-3, names=names)
+    print(f"dk53 worst gradient rel L2 error {worst[0]:.2e} ({worst[1]})")
+    assert net.saturated() == 0
     tr.step(B)
     assert net.launches > 300

@@ -76,6 +76,9 @@ SYMBOLS = {
     "yolo_loss_targets": (_I, [C.POINTER(DecodeGeom), C.POINTER(_VP), _VP, _I, _I, C.POINTER(LossParams), _VP, _VP, C.POINTER(_VP), _VP, _VP]),
     "yolo_train_flat_size": (_SZ, [_VP]),
     "yolo_train_init": (_I, [_VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "yolo_train_set_bn_momentum": (_I, [_VP, C.c_float]),
+    "yolo_nccl_unique_id": (_I, [_VP]),
+    "yolo_train_comm_init": (_I, [_VP, _VP, _I, _I, _SZ]),
     "yolo_train_forward_backward": (_I, [_VP, _VP, _I, _VP, _I, _I, C.POINTER(LossParams), _VP, _VP]),
     "yolo_train_apply": (_I, [_VP, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _VP]),
     "yolo_get_param": (_I, [_VP, C.c_char_p, _VP, _SZ, _I]),

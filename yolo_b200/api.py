@@ -209,7 +209,9 @@ class Net:
 
     def forward(self, is_train=False, data=None):
         if is_train:
-            raise NotImplementedError("training forward goes through the train-step API")
+            # the reference records the forward for autograd (car/YOLO.py:383-384) and calls backward on the losses; here the whole
+            # step is one fused call because BatchNorm statistics, losses and gradients never leave the device
+            raise NotImplementedError("train-mode forward is part of the fused step: use YOLO._train_batch / Trainer.forward_backward")
         x = self._to_device(data)
         H, W = self.spec["size"]
         if x.dtype == torch.float32 and x.dim() == 4 and tuple(x.shape[1:]) == (3, H, W):
@@ -348,14 +350,16 @@ def loss_targets(spec, heads, labels, scale, positive_weight, negative_weight, c
 
 
 class Trainer:
-    """Data-parallel training of a ``Net`` (fp32 CARNET), one process per GPU - the B200 shape of ``_init_train`` +
-    ``_train_batch`` + ``gluon.Trainer(..., 'adam').step(batch_size)`` (car/YOLO.py:157-207, 350-399).
+    """Data-parallel training of a ``Net`` (CARNET / CARLPNET, precision fp16x3 = fp32-grade on the tensor cores), one process per
+    GPU - the B200 shape of ``_init_train`` + ``_train_batch`` + ``gluon.Trainer(..., 'adam').step(batch_size)``
+    (car/YOLO.py:157-207, 350-399).
 
-    The flat parameter / gradient / Adam buffers are torch tensors (device-memory containers); when torch.distributed is
-    initialised the gradients are summed over ranks with ONE all-reduce (NCCL over NVLink) between backward and the update,
-    mirroring the kvstore reduction inside ``trainer.step``.  BatchNorm statistics stay per GPU like in the reference."""
+    The flat parameter / gradient / Adam buffers are torch tensors (device-memory containers).  When torch.distributed is
+    initialised with more than one rank, the library joins its own NCCL communicator (the 128-byte id travels through
+    torch.distributed) and sums the gradient over ranks bucket by bucket while the backward runs - the kvstore reduction inside
+    ``trainer.step``.  BatchNorm statistics stay per GPU like in the reference."""
 
-    def __init__(self, net, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
+    def __init__(self, net, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8, bucket_bytes=64 << 20, join_nccl=True):
         self.net, self.lib = net, net.lib
         self.lr, self.beta1, self.beta2, self.eps = float(learning_rate), float(beta1), float(beta2), float(epsilon)
         n = self.lib.yolo_train_flat_size(net._h)
@@ -364,9 +368,33 @@ class Trainer:
         with torch.cuda.device(dev):
             check(self.lib.yolo_train_init(net._h, C.c_void_p(self.P.data_ptr()), C.c_void_p(self.G.data_ptr()), C.c_void_p(self.M.data_ptr()),
                                            C.c_void_p(self.V.data_ptr()), n, _stream_ptr(dev)), net._h)
+        net._trainer = self              # the handle reads the flat buffers: keep them alive as long as the net
+        self.world, self.rank, self.nccl_joined = 1, 0, False
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.world, self.rank = dist.get_world_size(), dist.get_rank()
+            if join_nccl:
+                self._join_nccl(dist, int(bucket_bytes))
+
+    def _join_nccl(self, dist, bucket_bytes):
+        dev = self.net.device
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            check(self.lib.yolo_nccl_unique_id(C.c_void_p(uid.data_ptr())))
+        on_gpu = dist.get_backend() == "nccl"
+        t = uid.to(dev) if on_gpu else uid
+        dist.broadcast(t, src=0)
+        uid = t.cpu().contiguous()
+        with torch.cuda.device(dev):
+            check(self.lib.yolo_train_comm_init(self.net._h, C.c_void_p(uid.data_ptr()), self.rank, self.world, bucket_bytes), self.net._h)
+        self.nccl_joined = True
+
+    def set_bn_momentum(self, momentum):
+        check(self.lib.yolo_train_set_bn_momentum(self.net._h, float(momentum)), self.net._h)
 
     def forward_backward(self, images, labels, scale, positive_weight, negative_weight, car_rotate=False):
-        """images: (b,3,H,W) fp32 or (b,H,W,3) uint8; labels: (b,n_obj,6+num_class).  Returns the (5,b) losses (cuda)."""
+        """images: (b,3,H,W) fp32 or (b,H,W,3) uint8; labels: (b,n_obj,6+num_class).  Returns the (5,b) losses (cuda).
+        With the library's communicator joined the gradient buffer holds the sum over ranks when this stream reaches it."""
         net = self.net
         x = net._to_device(images).contiguous()
         layout = IN_NCHW_F32 if x.dtype == torch.float32 else IN_NHWC_U8
@@ -382,9 +410,11 @@ class Trainer:
         return losses
 
     def allreduce_grads(self):
+        """Sum of the gradients over ranks.  A no-op when the library reduced them during the backward (the default)."""
+        if self.nccl_joined or self.world == 1:
+            return
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.G, op=dist.ReduceOp.SUM)
+        dist.all_reduce(self.G, op=dist.ReduceOp.SUM)
 
     def step(self, batch_size):
         """``trainer.step(batch_size)``: gradients (already summed over ranks) are rescaled by 1/batch_size, then Adam."""
@@ -396,3 +426,19 @@ class Trainer:
         out = np.empty(shape, np.float32)
         check(self.lib.yolo_get_param(self.net._h, name.encode(), out.ctypes.data_as(C.c_void_p), out.size, int(grad)), self.net._h)
         return out
+
+    def calibrate_bn(self, images):
+        """Set every BatchNorm's running statistics to the batch statistics of ``images`` (one train-mode forward with momentum 0;
+        parameters untouched) - what synthetic random weights need to behave like a trained net."""
+        net = self.net
+        C_ = int(net.spec["slice_point"][-1])
+        lab = np.full((images.shape[0], 1, C_), -1.0, np.float32)
+        sc = {"score": 0.0, "box_yx": 0.0, "box_hw": 0.0, "rotate": 0.0, "class": 0.0}
+        self.set_bn_momentum(0.0)
+        self.forward_backward(images, lab, sc, 1.0, 1.0)
+        self.set_bn_momentum(0.9)
+        lr = self.lr
+        self.lr = 0.0
+        self.step(1)                     # lr 0: parameters stay, the inference epilogues are refolded with the new statistics
+        self.lr = lr
+        torch.cuda.current_stream(net.device).synchronize()

@@ -59,6 +59,7 @@ struct ConvDesc {
   void* out;  int out_dtype;  int Ho, Wo;  int out_cpitch, out_coff;  long long out_plane_stride;
   int upsample2;               // write every output pixel to the 2x2 block of a (2Ho, 2Wo) map
   int out_nchw;                // fp32 only: store as (N, Cout, Ho, Wo)
+  const float* dyn_scale;      // optional device scalar multiplied into the accumulator before scale/shift (dynamic gradient scale)
   int* sat_flag;               // optional device flag: |= 1 when a value leaves the fp16 range of the DT_F16X2 high plane
 };
 

@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
     sc[j] = ok && d.scale ? __ldg(d.scale + nb + j) : 1.f;
     sh[j] = ok && d.shift ? __ldg(d.shift + nb + j) : 0.f;
   }
+  const float dyn = d.dyn_scale ? __ldg(d.dyn_scale) : 1.f;
   const bool full4 = nb + 3 < d.Cout;
   const bool vec_out = full4 && !d.out_nchw && ((d.out_cpitch | d.out_coff) & 3) == 0;
   const bool vec_res = full4 && d.res && ((d.res_cpitch | d.res_coff) & 3) == 0;
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float y = fmaf(acc[i][j], sc[j], sh[j]);
+      float y = fmaf(acc[i][j] * dyn, sc[j], sh[j]);
       if (d.act == ACT_LEAKY) y = y > 0.f ? y : 0.1f * y;
       else if (d.act == ACT_RELU) y = fmaxf(y, 0.f);
       v[j] = y;

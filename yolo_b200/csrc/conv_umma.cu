@@ -71,7 +71,7 @@ struct UmmaParams {
   int accum;                                // fp32 output only: out += result (gradient buffers with several producers)
   float* stats;                             // optional [ceil(M/32)][2][Cout] per-warp column sums / sums of squares of the result (BatchNorm statistics)
   int* sat_flag;                            // optional: set to 1 when a value exceeds the fp16 range of the high plane
-  float bias_comp;                          // truncation-bias compensation added per drained partial, in ulps of the partial (0 = off)
+  float drain_gain;                         // 1 + truncation-bias compensation of one TMEM partial (1 = off)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -117,7 +117,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 //   7  C32I: Cin = 32 with PLANE-INTERLEAVED activations (pixel row = [hi(32) | lo(32)] = one 128-byte row instead of two 64-byte rows,
 //      which cost twice as much per byte to land).  One k-block = one filter tap, K' = 64: weight plane X = [w_hi | w_hi] gives hi*hi
 //      (k-steps 0,1 -> partial) and lo*hi (k-steps 2,3 -> correction), plane Y = [w_lo | 0] gives hi*lo (k-steps 0,1 -> correction).
-template <int MODE, bool OUT_F32, int KIND>
+template <int MODE, bool OUT_F32, int KIND, bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ UmmaParams p) {
@@ -413,17 +413,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint32_t v[32];
             tmem_ld_32x32b_x32(taddr + c * 32, v);
             tmem_ld_wait();
-            if (p.bias_comp != 0.f) {
-              // The tensor core's accumulator truncates toward zero: a partial that saw n full-magnitude MMA additions is short by
-              // ~n/2 ulp on average, with the SAME sign on every output - a coherent bias that the next layer's K-sum amplifies.
-              // Add the expected loss back (sign and exponent of the partial x bias_comp * 2^-23): the mean error vanishes.
+            // The tensor core's accumulator truncates toward zero: a partial that saw n full-magnitude MMA additions is short by
+            // ~n/2 ulp on average, with the SAME sign on every output - a coherent relative bias (measured -1e-7 per layer,
+            // profiles/r1_umma_precision.txt) that the next layer's K-sum amplifies.  drain_gain = 1 + expected loss adds it back
+            // for free in the round-to-nearest register accumulation (Darknet-53 head error 2.7e-4 -> 0.9e-4, profiles/r2_biascomp.txt).
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                acc[c][i] += fmaf(__uint_as_float(v[i] & 0xFF800000u), p.bias_comp, __uint_as_float(v[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) acc[c][i] += __uint_as_float(v[i]);
-            }
+            for (int i = 0; i < 32; ++i) acc[c][i] = fmaf(__uint_as_float(v[i]), p.drain_gain, acc[c][i]);
           }
         }
         tc_fence_before();
@@ -457,7 +452,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       //  instruction fetch - profiles/r1_ncu_summary.md)
       const int m = m0 + row;
       const bool valid = m < p.M && p.dbg_nostore != 2;
-      if (!valid && !p.stats) continue;                    // with statistics the whole warp takes part in the shuffles
+      if (!valid && !STATS) continue;                      // with statistics the whole warp takes part in the shuffles
       size_t pix[4];
       int npix = 1;
       if (p.upsample2) {
@@ -492,7 +487,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           }
         }
-        if (p.stats) {
+        if constexpr (STATS) {
           // BatchNorm batch statistics of the raw convolution output (training forward): per-warp column sums of the 32 rows
           // by a transposing shuffle butterfly; the finalize kernel adds the per-warp partials in a fixed order (deterministic)
           float t[32];
@@ -927,9 +922,9 @@ int device_sm_count(int* sms) {
   return YOLO_OK;
 }
 
-template <int MODE, bool OUT_F32, int KIND>
-static int launch_mode3(const UmmaConv& u, const UmmaParams& p, int smem_bytes, int num_sms, cudaStream_t st) {
-  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&conv_umma_kernel<MODE, OUT_F32, KIND>), SMEM_LIMIT);
+template <int MODE, bool OUT_F32, int KIND, bool STATS>
+static int launch_mode4(const UmmaConv& u, const UmmaParams& p, int smem_bytes, int num_sms, cudaStream_t st) {
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&conv_umma_kernel<MODE, OUT_F32, KIND, STATS>), SMEM_LIMIT);
   if (rc) return rc;
   if (KIND == 6) {
     int pairs = num_sms / 2;
@@ -945,17 +940,26 @@ static int launch_mode3(const UmmaConv& u, const UmmaParams& p, int smem_bytes, 
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    YB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<MODE, OUT_F32, KIND>, *reinterpret_cast<const CUtensorMap*>(u.map_a),
+    YB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<MODE, OUT_F32, KIND, STATS>, *reinterpret_cast<const CUtensorMap*>(u.map_a),
                                *reinterpret_cast<const CUtensorMap*>(u.map_b), p));
     ++g_launches;
     return YOLO_OK;
   }
   const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-  conv_umma_kernel<MODE, OUT_F32, KIND><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
-                                                                               *reinterpret_cast<const CUtensorMap*>(KIND == 5 ? u.map_bw : u.map_b), p);
+  conv_umma_kernel<MODE, OUT_F32, KIND, STATS><<<grid, NUM_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(u.map_a),
+                                                                                      *reinterpret_cast<const CUtensorMap*>(KIND == 5 ? u.map_bw : u.map_b), p);
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
+}
+// BatchNorm statistics in the epilogue exist for the training forward only: fp16x3, 16-bit output
+template <int MODE, bool OUT_F32, int KIND>
+static int launch_mode3(const UmmaConv& u, const UmmaParams& p, int smem_bytes, int num_sms, cudaStream_t st) {
+  if constexpr (MODE == 2 && !OUT_F32) {
+    if (p.stats) return launch_mode4<MODE, OUT_F32, KIND, true>(u, p, smem_bytes, num_sms, st);
+  }
+  if (p.stats) return fail(YOLO_E_UNSUPPORTED, "umma: epilogue statistics need fp16x3 and a 16-bit output");
+  return launch_mode4<MODE, OUT_F32, KIND, false>(u, p, smem_bytes, num_sms, st);
 }
 template <int MODE>
 static int launch_mode(const UmmaConv& u, const UmmaParams& p, int kind, int smem_bytes, int num_sms, cudaStream_t st) {
@@ -972,7 +976,7 @@ static int launch_mode(const UmmaConv& u, const UmmaParams& p, int kind, int sme
   return f32 ? launch_mode3<MODE, true, 0>(u, p, smem_bytes, num_sms, st) : launch_mode3<MODE, false, 0>(u, p, smem_bytes, num_sms, st);
 }
 
-int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, const UmmaExtra* ex) {
+int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, UmmaExtra* ex) {
   if (!u.enabled) return fail(YOLO_E_STATE, "umma: tensor maps not built");
   if (d.N > u.max_batch) return fail(YOLO_E_SHAPE, "umma: batch %d exceeds the tensor map's %d", d.N, u.max_batch);
   const UmmaEnv& env = umma_env();
@@ -1022,7 +1026,13 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, cons
   if (kind == 7) p.flush = 4;                              // two hi*hi MMAs per tap -> 8 per partial
   if ((kind == 5 || kind == 6) && (env.hhlast >= 0 ? env.hhlast == 1 : kind == 6)) { p.hh_last = 1; p.flush = 2; }   // ... or two in hh-last order
   if (env.flush >= 1 && env.flush <= 64) p.flush = env.flush;
-  p.bias_comp = (env.bias_comp >= 0.f ? env.bias_comp : 0.f) * 1.1920929e-7f;      // ulps -> 2^-23
+  {
+    // truncation-bias compensation: expected relative loss of one partial ~ delta * 2^-23 per 8 full-magnitude MMA additions
+    // (delta calibrated on Darknet-53, profiles/r2_biascomp.txt; YOLO_B200_BIASCOMP overrides, 0 = off)
+    const float delta = env.bias_comp >= 0.f ? env.bias_comp : 1.4f;
+    const int hh_per_partial = (kind == 7 ? 2 : p.bk / UMMA_K) * p.flush;
+    p.drain_gain = 1.f + delta * 1.1920929e-7f * (float)hh_per_partial / 8.f;
+  }
   p.dbg_pairs = env.dbg_pairs;
   p.dbg_nostore = env.dbg_nostore;
   int stages = (SMEM_LIMIT - 1024 - aux_bytes) / stage_bytes;
@@ -1036,7 +1046,10 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, cons
   p.res_plane_stride = d.res_plane_stride;
   p.out_plane_stride = d.out_plane_stride;
   p.sat_flag = d.sat_flag;
-  if (ex) { p.acc_scale_dev = ex->acc_scale_dev; p.accum = ex->accum; p.stats = ex->stats; }
+  if (ex) {
+    p.acc_scale_dev = ex->acc_scale_dev; p.accum = ex->accum; p.stats = ex->stats;
+    ex->stats_groups_out = (size_t)(kind == 6 ? 8 * ((m_tiles + 1) / 2) : 4 * m_tiles);
+  }
   if (p.accum && d.out_dtype != DT_F32) return fail(YOLO_E_UNSUPPORTED, "umma: accumulate-into-output is an fp32 epilogue");
   if (d.out_dtype != DT_F32 && (((d.out_cpitch | d.out_coff) & 7) || d.Cout % 8)) return fail(YOLO_E_UNSUPPORTED, "umma: 16-bit output needs 16-byte aligned channel slices and Cout %% 8 == 0");
   if (d.res && ((d.res_cpitch | d.res_coff) & 7)) return fail(YOLO_E_UNSUPPORTED, "umma: residual needs 16-byte aligned channel slices");

@@ -32,6 +32,7 @@ struct UmmaExtra {
   const float* acc_scale_dev = nullptr;   // second accumulator scale read from device memory (dynamic gradient scale)
   int accum = 0;                          // fp32 output: out += result
   float* stats = nullptr;                 // [umma_stats_groups(M)][2][Cout] per-warp column sums / sums of squares of the result
+  size_t stats_groups_out = 0;            // set by the launcher: row groups (of 32 pixels) the kernel wrote statistics for
 };
 
 // w_oihw may be null: the packed planes are then zero-filled and written later by umma_pack_device
@@ -44,7 +45,7 @@ void umma_set_prescale(UmmaConv& u, float wmax, int top);
 // *sat_flag |= 2 when a scaled weight leaves the fp16 range.
 int umma_pack_device(const UmmaConv& u, const float* w_mat, int w_cin, int w_cout, int cout_pad, bool dgrad, int* sat_flag, cudaStream_t st);
 int umma_build_maps(UmmaConv& u, void* in_base, int max_batch, int H, int W, int C, int cpitch, int coff);
-int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, const UmmaExtra* ex = nullptr);
+int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, UmmaExtra* ex = nullptr);
 size_t umma_stats_groups(int M);
 void umma_release(UmmaConv& u);
 

@@ -339,7 +339,7 @@ static void layout_workspace(yolo_handle* h) {
 static void* resolve(const yolo_handle* h, const View& v, const void* input, void* const* outputs) {
   if (v.buf >= 0) return h->ws + h->bufs[v.buf].offset;
   if (v.buf == -1) return const_cast<void*>(input);
-  return outputs[-2 - v.buf];
+  return outputs ? outputs[-2 - v.buf] : nullptr;
 }
 
 // ConvDesc of one planned convolution for `batch` images (inference epilogue: folded BN, activation, residual, placement)
@@ -404,7 +404,7 @@ extern "C" int yolo_destroy(yolo_handle* h) {
   if (h->dparams) cudaFree(h->dparams);
   if (h->stage) cudaFree(h->stage);
   if (h->d_flags) cudaFree(h->d_flags);
-  train_release(h);
+  train_release(h, false);
   for (auto& op : h->ops) umma_release(op.umma);
   delete h;
   return YOLO_OK;
@@ -454,6 +454,7 @@ extern "C" int yolo_finalize_params(yolo_handle* h, void* stream) {
     if (!p.loaded) return hfail(h, fail(YOLO_E_STATE, "finalize: parameter '%s' was never loaded", p.name.c_str()));
   YB_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  train_release(h, false);                   // a trainer attached to the previous parameters is stale
   // size the device arena
   size_t total = 0;
   auto take = [&](size_t nfloat) { size_t o = total; total += ((nfloat * 4 + 255) & ~(size_t)255); return o; };
@@ -492,7 +493,7 @@ extern "C" int yolo_finalize_params(yolo_handle* h, void* stream) {
         for (int r = 0; r < kh; ++r)
           for (int s2 = 0; s2 < kw; ++s2)
             wd[((size_t)(r * kw + s2) * cin + c) * op.cout_pad + o] = W[(((size_t)o * cin + c) * kh + r) * kw + s2];
-    op.w_f32 = reinterpret_cast<float*>(dbase + slots[i].w);
+    op.w_f32 = op.w_f32_own = reinterpret_cast<float*>(dbase + slots[i].w);
     std::vector<float> sc, sh;
     op.scale = op.shift = op.pre_scale = op.pre_shift = nullptr;
     if (op.p_bn >= 0) {

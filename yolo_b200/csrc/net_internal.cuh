@@ -48,6 +48,7 @@ struct Op {
   int p_weight = -1, p_bias = -1, p_bn = -1, p_prebn = -1;   // index of the FIRST param of each group
   // device parameter pointers (valid after finalize)
   float* w_f32 = nullptr;
+  float* w_f32_own = nullptr;  // the handle's own copy in the parameter arena (w_f32 points into the trainer's flat buffer while training)
   int cout_pad = 0;
   float *scale = nullptr, *shift = nullptr, *pre_scale = nullptr, *pre_shift = nullptr;
   UmmaConv umma;           // tensor-core path state (tensor maps, packed weights); engaged iff umma.enabled
@@ -89,6 +90,6 @@ inline int hfail(yolo_handle* h, int code) {
   if (h) h->err = tls_error();
   return code;
 }
-void train_release(yolo_handle* h);
+void train_release(yolo_handle* h, bool writeback = true);      // writeback: copy the trained parameters into the handle's own copies
 void fill_conv_desc(const yolo_handle* h, const Op& op, int batch, const void* input, void* const* outputs, ConvDesc& d);
 }  // namespace yb

@@ -105,7 +105,7 @@ class YOLO:
         raise ValueError("mode must be 'top1' or 'nms'")
 
 
-    # -------------------- Training Part (targets + losses; backward/optimizer: next round) -------------------- #
+    # -------------------- Training Part -------------------- #
     def _loss_mask_and_get_loss(self, y_, car_by, car_rotate=False, with_grad=False):
         """GPU replacement of ``_loss_mask`` + ``_score_weight`` + ``_get_loss`` (car/YOLO.py:385-392, 450-498) for one device:
         y_ = list of head tensors from ``net.forward``, car_by = labels (b, num_object, 6+num_class).
@@ -130,11 +130,14 @@ class YOLO:
         if not hasattr(self, "trainer"):
             self._init_train()
         if len(bxs) != 1 or len(car_bys) != 1:
-            raise ValueError("one process per GPU: pass this rank's slice as single-element lists")
+            raise ValueError(f"one process per GPU (torchrun contract, INTEGRATION.md): pass this rank's slice as single-element lists, "
+                             f"got {len(bxs)} entries for ctx {self.ctx}")
         self.last_losses = self.trainer.forward_backward(bxs[0], car_bys[0], self.scale, self.positive_weight, self.negative_weight, car_rotate)
         self.trainer.allreduce_grads()
         self.trainer.step(self.global_batch_size)
         self.backward_counter += 1
+
+    train_step = _train_batch          # north-star name of the same call
 
 
 class CarLPYOLO(YOLO):

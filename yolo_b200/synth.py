@@ -37,3 +37,20 @@ def random_params(param_shapes, seed=0, obj_bias=-4.0, channels_per_anchor=None)
         else:
             raise KeyError(name)
     return p
+
+
+def calibrated_params(net, frames, seed=0, channels_per_anchor=None):
+    """Random-init parameters whose BatchNorm running statistics are the batch statistics of ``frames`` on this very network -
+    one train-mode forward on the GPU (Trainer.calibrate_bn).  Without it 23 residual blocks with running_var = 1 let the
+    activations grow by orders of magnitude and every sigmoid saturates.  Loads them into ``net`` and returns the dict."""
+    from .api import Trainer
+    p = random_params(net.param_shapes(), seed=seed, channels_per_anchor=channels_per_anchor)
+    net.load_params(p)
+    tr = Trainer(net, join_nccl=False)
+    tr.calibrate_bn(frames)
+    for name, shape in net.param_shapes():
+        if name.endswith((".running_mean", ".running_var")):
+            p[name] = tr.get_param(name, shape)
+    net.load_params(p)                   # also releases the trainer (its arena is several GB at large batch)
+    net._trainer = None
+    return p
