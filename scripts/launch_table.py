@@ -40,8 +40,10 @@ def main():
     rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10 and r[0].isdigit()]
     passes = float(sys.argv[2]) if len(sys.argv) > 2 else 3
     names = [r[4] for r in rows]
-    start = [i for i, n in enumerate(names) if "stem3x3" in n][0]
-    order = rows[start:] + rows[:start]
+    # the LAST complete step of the capture: 75 conv launches + decode_kernel<0>
+    last = [i for i, n in enumerate(names) if "decode_kernel" in n][-1]
+    order = rows[last - 75:last + 1]
+    assert "stem3x3" in order[0][4], order[0][4]
     convs = dk53_convs()
     ci, tot, tot_fl = 0, 0.0, 0.0
     groups = {}

@@ -901,7 +901,7 @@ extern "C" int yolo_train_forward_backward(yolo_handle* h, const void* input, in
       d.shift = nullptr;
       d.out = L.z; d.out_dtype = DT_F16X2; d.out_cpitch = C; d.out_coff = 0; d.out_plane_stride = L.z_ps;
     } else {
-      d.shift = T->P + L.o_bias;                                  // head convs: conv + bias is the output itself
+      d.shift = L.has_bias ? T->P + L.o_bias : nullptr;          // head convs: conv + bias is the output itself
       d.out = L.zf; d.out_dtype = DT_F32; d.out_cpitch = C; d.out_coff = 0; d.out_plane_stride = 0;
     }
     const int lay = op.in.buf == -1 ? lay_in : 0;
@@ -1020,7 +1020,7 @@ extern "C" int yolo_train_forward_backward(yolo_handle* h, const void* input, in
     } else {
       // head conv (no BatchNorm, 90 / 10 channels): fp32 FFMA kernels on dz = d loss / d head
       float* dz = T->dheads[-2 - op.out.buf];
-      colsum_kernel<<<(C + 31) / 32, 256, 0, st>>>(dz, M, C, T->G + L.o_bias);
+      if (L.has_bias) colsum_kernel<<<(C + 31) / 32, 256, 0, st>>>(dz, M, C, T->G + L.o_bias);
       const int slabs = std::max(1, std::min(M / 512, 64));
       const size_t kn = (size_t)K * op.cout_pad;
       dim3 gw((K + 63) / 64, (op.cout_pad + 63) / 64, slabs);
