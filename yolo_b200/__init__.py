@@ -5,7 +5,8 @@ the reference's drivers expect (``YOLO.predict``, ``predict_LP``, ``net.forward`
 """
 from ._lib import YoloError, load as load_library  # noqa: F401
 from .api import Net, NDArray, Trainer, decode_top1, decode_nms, decode_lp, loss_targets  # noqa: F401
-from .drivers import YOLO, CarLPYOLO, LicencePlateDetectioin, get_ctx  # noqa: F401
+from .drivers import YOLO, CarLPYOLO, LicencePlateDetectioin, get_ctx, init_NN  # noqa: F401
+from . import mxnet_io  # noqa: F401
 
 __all__ = ["Net", "NDArray", "Trainer", "decode_top1", "decode_nms", "decode_lp", "loss_targets", "YOLO", "CarLPYOLO", "LicencePlateDetectioin",
-           "get_ctx", "YoloError", "load_library"]
+           "get_ctx", "init_NN", "mxnet_io", "YoloError", "load_library"]

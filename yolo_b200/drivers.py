@@ -34,6 +34,24 @@ def get_ctx(gpu):
     return ctx
 
 
+def init_NN(target, weight, ctx=None, seed=0):
+    """yolo_gluon.init_NN (yolo_modules/yolo_gluon.py:172-201): load an MXNet ``collect_params().save`` / export ``.params`` file into
+    ``target`` (an ``api.Net``); if that fails, fall back to Xavier initialisation like the reference does (and say so)."""
+    from . import mxnet_io, synth
+    print("use pretrain weight: %s" % weight)
+    try:
+        params = mxnet_io.load_gluon_params(weight, target.net_type, target.spec, target.param_shapes())
+        target.load_params(params)
+        print("Load Pretrain Successfully")
+        return True
+    except Exception as e:      # noqa: BLE001  (the reference catches everything here)
+        print("Load Pretrain Failed, Use Xavier initializer")
+        print(str(e).split("\n")[0])
+        C = target.spec["slice_point"][-1] if "slice_point" in target.spec else None
+        target.load_params(synth.random_params(target.param_shapes(), seed=seed, channels_per_anchor=C))
+        return False
+
+
 def _load_spec(args, spec):
     if spec is None:
         with open(os.path.join(args.version, "spec.yaml")) as f:
@@ -72,7 +90,7 @@ class YOLO:
         self._init_area()
         self.version = getattr(args, "version", None)
         self.precision, self.max_batch = precision, max_batch
-        self._init_net(spec, params)
+        self._init_net(spec, params, getattr(args, "weight", None))
 
     def _init_step(self):                                  # car/YOLO.py:112-116
         self.steps = api.init_steps(self.spec)
@@ -81,10 +99,12 @@ class YOLO:
         h, w = self.size
         self.area = [int(h * w / step ** 2) for step in self.steps]
 
-    def _init_net(self, spec, params):                     # car/YOLO.py:91-110
+    def _init_net(self, spec, params, weight=None):        # car/YOLO.py:91-110
         self.net = api.Net(self.net_type, spec, self.precision, self.max_batch, self.ctx[0])
         if params is not None:
             self.net.load_params(params)
+        elif weight:                                       # args.weight: an MXNet .params file (car/YOLO.py:98-100)
+            init_NN(self.net, weight, self.ctx)
 
     # -------------------- Validation Part -------------------- #
     def predict(self, batch_out, mode="top1", score_thr=0.5, iou_thr=0.45, max_out=100, max_cand=1024, return_index=False):
