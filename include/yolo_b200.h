@@ -150,8 +150,13 @@ int  yolo_forward(yolo_handle* h, const void* input, int batch, int in_layout,
                   void* const* outputs, void* stream);
 
 /* fp16x3 range check.  The 16-bit activation format of YOLO_PREC_FP16X3 stores v = hi + lo with an fp16 high plane: |v| > 65504
- * saturates.  Saturation is never silent: every kernel that writes the format ORs bit 0 into a device flag of the handle
- * (bit 1: a weight left the fp16 range when the training step re-packed it).  Reads AND CLEARS the flags; synchronises `stream`. */
+ * saturates.  Saturation is never silent: every kernel that writes the format ORs a bit into a device flag word of the handle
+ * (which bit tells where).  Reads AND CLEARS the flags; synchronises `stream`. */
+#define YOLO_SAT_ACT_CONV  1   /* activation written by a tensor-core convolution epilogue            */
+#define YOLO_SAT_WEIGHT    2   /* weight re-packed by the training step                                */
+#define YOLO_SAT_ACT_FFMA  4   /* activation written by an FFMA convolution / stem / pool              */
+#define YOLO_SAT_ACT_BN    8   /* activation written by the training step's normalise pass             */
+#define YOLO_SAT_GRAD     16   /* scaled pre-activation gradient written by the BatchNorm backward     */
 int  yolo_check_saturation(yolo_handle* h, int32_t* flags_out, void* stream);
 
 /* Debug/parity: copy an internal activation (by oracle layer name) to host as NCHW fp32. */

@@ -221,3 +221,87 @@ def train_step(net, spec, params, x, labels, hp, lr=0.001, batch_size=None, adam
             new_params[k] = np.asarray(v, np.float32)
     return dict(losses=np.stack([l.detach().numpy() for l in losses]), grads=grads, params=new_params, adam=new_adam, assign=assign,
                 heads=[h.detach().numpy() for h in heads])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# licence-plate pose targets and losses (licence_plate/LP_detection.py:259-360, car_and_LP/YOLO.py:124-131,265-304)
+# ---------------------------------------------------------------------------------------------------------
+LP_V1_HPARAMS = dict(scale={"LP_score": 0.1, "LP_xy": 10.0, "LP_z": 1.0, "LP_r": 0.1, "LP_class": 0.0},
+                     LP_positive_weight=1.0, LP_negative_weight=0.1)          # car_and_LP/v1/spec.yaml:43,51-52
+
+
+def find_best_LP(spec, L, step):
+    """LP_detection.py:259-283: cell (h, w) = clip(int(L[8] / step)), clip(int(L[7] / step)); targets X/1000, Y/1000, Z/1000 and
+    sigma^-1(r_i / r_max_i / 2 + 0.5) (nd_inv_sigmoid = -log(1/x - 1), yolo_gluon.py:365-367), fp32 op by op."""
+    f = np.float32
+    h_max, w_max = spec["size"][0] // step - 1, spec["size"][1] // step - 1
+    hf = int(np.clip(int(f(L[8]) / f(step)), 0, h_max))
+    wf = int(np.clip(int(f(L[7]) / f(step)), 0, w_max))
+    t = [f(L[1]) / f(1000.0), f(L[2]) / f(1000.0), f(L[3]) / f(1000.0)]
+    for i in range(3):
+        rmax = f(f(spec["LP_r_max"][i]) * f(np.pi) / f(180.0))
+        x = f(f(f(L[4 + i]) / rmax) / f(2.0)) + f(0.5)
+        t.append(f(-np.log(f(f(1.0) / x) - f(1.0), dtype=np.float32)))
+    return (hf, wf), np.asarray(t, np.float32)
+
+
+def loss_mask_LP(spec, labels, step):
+    """LP_detection.py:285-313 -> ([score, pose_xy, pose_z, pose_r, LP_class] dense targets (B,Hs,Ws,k), mask).
+    A later label overwrites pose/score of an earlier one in the same cell; class one-hots accumulate (the reference never clears them)."""
+    labels = np.asarray(labels, np.float32)
+    B = labels.shape[0]
+    hs, ws, nc = spec["size"][0] // step, spec["size"][1] // step, spec["LP_num_class"]
+    score, mask = np.zeros((B, hs, ws, 1), np.float32), np.zeros((B, hs, ws, 1), np.float32)
+    xy, z, r = np.zeros((B, hs, ws, 2), np.float32), np.zeros((B, hs, ws, 1), np.float32), np.zeros((B, hs, ws, 3), np.float32)
+    cls = np.zeros((B, hs, ws, nc), np.float32)
+    for b in range(B):
+        for L in labels[b]:
+            if L[0] < 0:
+                continue
+            (hf, wf), p = find_best_LP(spec, L, step)
+            score[b, hf, wf] = 1.0
+            mask[b, hf, wf] = 1.0
+            xy[b, hf, wf] = p[:2]
+            z[b, hf, wf] = p[2]
+            r[b, hf, wf] = p[3:]
+            cls[b, hf, wf, int(L[-1])] = 1
+    return [score, xy, z, r, cls], mask
+
+
+def get_loss_LP(spec, lp_x, targets, mask, hp):
+    """LP_detection.py:354-360 with the gluon loss definitions; lp_x: (B,Hs,Ws,ch) torch tensor (may require grad)."""
+    sp = spec["LP_slice_point"]
+    xs, i = [], 0
+    for pt in sp:
+        xs.append(lp_x[..., i:pt]); i = pt
+    y = [torch.as_tensor(t) for t in targets]
+    m = torch.as_tensor(mask)
+    sw = torch.where(m > 0, torch.full_like(m, hp["LP_positive_weight"]), torch.full_like(m, hp["LP_negative_weight"]))
+    sc = hp["scale"]
+
+    def logistic(p, lab, w):
+        lab = 2 * lab - 1
+        return _mean_nb((torch.relu(-p * lab) + torch.nn.functional.softplus(-torch.abs(p * lab))) * w)
+
+    def huber(p, lab, w, rho=1.0):
+        d = torch.abs(lab - p)
+        return _mean_nb(torch.where(d > rho, d - 0.5 * rho, (0.5 / rho) * d * d) * w)
+
+    def softmax_ce(p, lab, w):
+        return _mean_nb(-(torch.log_softmax(p, dim=-1) * lab).sum(dim=-1, keepdim=True) * w)
+
+    return (logistic(xs[0], y[0], sw * sc["LP_score"]), huber(xs[1], y[1], m * sc["LP_xy"]), huber(xs[2], y[2], m * sc["LP_z"]),
+            huber(xs[3], y[3], m * sc["LP_r"]), softmax_ce(xs[4], y[4], m * sc["LP_class"]))
+
+
+def synthetic_LP_labels(batch, size, nobj=1, seed=5, p_box=0.7, num_class=3):
+    """LP label rows [flag, X, Y, Z (mm), r1, r2, r3 (rad), pixel x, pixel y, class] (render layout read by _find_best_LP)."""
+    rng = np.random.default_rng(seed)
+    lab = np.full((batch, nobj, 10), -1.0, np.float32)
+    for b in range(batch):
+        for j in range(nobj):
+            if rng.random() < p_box:
+                lab[b, j] = [1, rng.uniform(-2000, 2000), rng.uniform(-1000, 1000), rng.uniform(3000, 20000), rng.uniform(-0.6, 0.6),
+                             rng.uniform(-0.8, 0.8), rng.uniform(-0.6, 0.6), rng.uniform(0, size[1] - 1), rng.uniform(0, size[0] - 1),
+                             rng.integers(0, num_class)]
+    return lab

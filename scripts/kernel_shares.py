@@ -1,4 +1,5 @@
-"""Aggregate an ncu gpu__time_duration CSV by kernel name (template arguments kept): count, total ms, share."""
+"""Aggregate an ncu gpu__time_duration CSV by kernel name (template arguments kept): count, total ms, share.
+Usage: kernel_shares.py launches.csv [N]   (N: only the last N launches, e.g. one training step)"""
 import csv
 import sys
 from collections import defaultdict
@@ -6,7 +7,10 @@ from collections import defaultdict
 with open(sys.argv[1]) as f:
     lines = [l for l in f if l.startswith('"')]
 tot = defaultdict(lambda: [0, 0.0])
-for r in csv.DictReader(lines):
+rows = list(csv.DictReader(lines))
+if len(sys.argv) > 2:
+    rows = rows[-int(sys.argv[2]):]
+for r in rows:
     name = r["Kernel Name"]
     short = name[name.find("void ") + 5 if "void " in name else 0:name.find("(")]
     v = float(r["Metric Value"].replace(",", ""))

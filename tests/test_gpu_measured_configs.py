@@ -43,8 +43,10 @@ def test_cfg2_dk53_416_batch32():
     check_top1_indices(idx, oidx, ref32, margin=max(2e-4, 4 * noise))
     same = idx == oidx
     assert same.sum() >= B - 1
-    assert np.abs(pred[same][:, :4] - opred[same][:, :4]).max() <= 1e-4              # score, y, x, h
-    assert np.abs(pred[same][:, 4] - opred[same][:, 4]).max() <= max(1e-4, 4 * noise)   # w = exp(tw) * anchor carries the logit error 1:1
+    assert np.abs(pred[same][:, :3] - opred[same][:, :3]).max() <= 1e-4              # score, y, x
+    # h, w = exp(t) * anchor carry the logit error 1:1 (relative): cuda-vs-fp32-oracle <= (2 + 1) x the fp32 oracle's own noise
+    rel = np.abs(pred[same][:, 3:5] - opred[same][:, 3:5]) / np.maximum(np.abs(opred[same][:, 3:5]), 1e-6)
+    assert rel.max() <= max(1e-4, 3.5 * noise), (rel.max(), noise)
 
 
 def test_cfg3_lpdensenet_batch64():
@@ -96,7 +98,9 @@ def test_cfg5_car_and_lp_608_batch16():
     opred, oidx = decode.predict(spec, ref32[:3], return_index=True)
     check_top1_indices(idx, oidx, ref32[:3], margin=max(2e-4, 4 * noise))
     same = idx == oidx
-    assert np.abs(pred[same][:, :4] - opred[same][:, :4]).max() <= 1e-4
+    assert np.abs(pred[same][:, :3] - opred[same][:, :3]).max() <= 1e-4
+    rel = np.abs(pred[same][:, 3:5] - opred[same][:, 3:5]) / np.maximum(np.abs(opred[same][:, 3:5]), 1e-6)
+    assert rel.max() <= max(1e-4, 3.5 * noise), (rel.max(), noise)
     lrows, lidx = y.predict_LP([out[3]], return_index=True)
     olr, oli = decode.predict_LP_batch(spec, ref32[3], return_index=True)
     lsame = lidx == oli

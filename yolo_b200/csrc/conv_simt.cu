@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
       else for (int j = 0; j < 4 && nb + j < d.Cout; ++j) store1f<FO>(op + j, d.out_plane_stride, v[j], sat);
     }
   }
-  if (sat && d.sat_flag) atomicOr(d.sat_flag, 1);
+  if (sat && d.sat_flag) atomicOr(d.sat_flag, YOLO_SAT_ACT_FFMA);
 }
 
 template <class FI, class FO>
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
       } else if (m < args.M) store4f<FO>(op + o0 + j4, d.out_plane_stride, v, sat);
     }
   }
-  if (sat && d.sat_flag) atomicOr(d.sat_flag, 1);
+  if (sat && d.sat_flag) atomicOr(d.sat_flag, YOLO_SAT_ACT_FFMA);
   if (staged) {
     __syncthreads();
     const int rows = min((int)blockDim.x, args.M - m_blk0);

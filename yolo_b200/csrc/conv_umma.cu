@@ -71,7 +71,7 @@ struct UmmaParams {
   int accum;                                // fp32 output only: out += result (gradient buffers with several producers)
   float* stats;                             // optional [ceil(M/32)][2][Cout] per-warp column sums / sums of squares of the result (BatchNorm statistics)
   int* sat_flag;                            // optional: set to 1 when a value exceeds the fp16 range of the high plane
-  float drain_gain;                         // 1 + truncation-bias compensation of one TMEM partial (1 = off)
+  float bias_comp;                          // truncation-bias compensation: relative amount added back to the accumulated sum (0 = off)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -413,12 +413,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint32_t v[32];
             tmem_ld_32x32b_x32(taddr + c * 32, v);
             tmem_ld_wait();
-            // The tensor core's accumulator truncates toward zero: a partial that saw n full-magnitude MMA additions is short by
-            // ~n/2 ulp on average, with the SAME sign on every output - a coherent relative bias (measured -1e-7 per layer,
-            // profiles/r1_umma_precision.txt) that the next layer's K-sum amplifies.  drain_gain = 1 + expected loss adds it back
-            // for free in the round-to-nearest register accumulation (Darknet-53 head error 2.7e-4 -> 0.9e-4, profiles/r2_biascomp.txt).
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[c][i] = fmaf(__uint_as_float(v[i]), p.drain_gain, acc[c][i]);
+            for (int i = 0; i < 32; ++i) acc[c][i] += __uint_as_float(v[i]);
           }
         }
         tc_fence_before();
@@ -481,7 +477,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const float sc[4] = {a.x, a.y, a.z, a.w}, sh[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float t = fmaf(y[4 * q + e] * acc_scale, sc[e], sh[e]);
+              // The tensor core's accumulator truncates toward zero: a TMEM partial that saw n full-magnitude MMA additions is short by
+              // ~n/2 ulp on average, with the SAME sign on every output - a coherent relative bias (measured -1e-7 per layer,
+              // profiles/r1_umma_precision.txt) that the next layer's K-sum amplifies.  Every partial carries the same expected
+              // relative loss, so it is added back once, here (round-to-nearest of y*(1+c) is unbiased even for c < 1 ulp):
+              // Darknet-53 head error vs fp64 2.7e-4 -> 0.9e-4 (profiles/r2_biascomp.txt).
+              float t = fmaf(fmaf(y[4 * q + e], p.bias_comp, y[4 * q + e]) * acc_scale, sc[e], sh[e]);
               t = leaky ? fmaxf(t, 0.1f * t) : (relu ? fmaxf(t, 0.f) : t);
               y[4 * q + e] = t;
             }
@@ -561,7 +562,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 float a = y[i], b = y[i + 1];
                 if (pl == 0) {
                   // the high plane saturates at the fp16 range: flagged, never silent (yolo_check_saturation)
-                  if (fmaxf(fabsf(a), fabsf(b)) > kF16Max) saturated = 1;
+                  if (i < nvalid && fmaxf(fabsf(a), fabsf(b)) > kF16Max) saturated = 1;      // columns >= nvalid hold stale TMEM, never stored
                   a = fminf(fmaxf(a, -kF16Max), kF16Max); b = fminf(fmaxf(b, -kF16Max), kF16Max);
                 }
                 __half2 h = __floats2half2_rn(a, b);
@@ -587,7 +588,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
-    if (saturated && p.sat_flag) atomicOr(p.sat_flag, 1);
+    if (saturated && p.sat_flag) atomicOr(p.sat_flag, YOLO_SAT_ACT_CONV);
   }
 
   tc_fence_before();
@@ -815,7 +816,7 @@ pack_fwd_kernel(const float* __restrict__ w_mat, int K, int Cin, int Cout, int c
       out[((size_t)rows + o) * Kp + k] = lo;
     }
   }
-  if (sat && sat_flag) atomicOr(sat_flag, 2);
+  if (sat && sat_flag) atomicOr(sat_flag, YOLO_SAT_WEIGHT);
 }
 __global__ void __launch_bounds__(256)
 pack_dgrad_kernel(const float* __restrict__ w_mat, int kh, int kw, int Cin, int Cout, int cout_pad, float prescale,
@@ -834,7 +835,7 @@ pack_dgrad_kernel(const float* __restrict__ w_mat, int kh, int kw, int Cin, int 
     out[(size_t)c * Kp + (size_t)tap2 * Cout + o] = hi;
     out[((size_t)rows + c) * Kp + (size_t)tap2 * Cout + o] = lo;
   }
-  if (sat && sat_flag) atomicOr(sat_flag, 2);
+  if (sat && sat_flag) atomicOr(sat_flag, YOLO_SAT_WEIGHT);
 }
 
 void umma_set_prescale(UmmaConv& u, float wmax, int top) { set_prescale(u, wmax, top); }
@@ -1031,7 +1032,7 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, Umma
     // (delta calibrated on Darknet-53, profiles/r2_biascomp.txt; YOLO_B200_BIASCOMP overrides, 0 = off)
     const float delta = env.bias_comp >= 0.f ? env.bias_comp : 1.4f;
     const int hh_per_partial = (kind == 7 ? 2 : p.bk / UMMA_K) * p.flush;
-    p.drain_gain = 1.f + delta * 1.1920929e-7f * (float)hh_per_partial / 8.f;
+    p.bias_comp = delta * 1.1920929e-7f * (float)hh_per_partial / 8.f;
   }
   p.dbg_pairs = env.dbg_pairs;
   p.dbg_nostore = env.dbg_nostore;

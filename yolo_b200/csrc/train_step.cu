@@ -250,7 +250,7 @@ bn_act_fwd_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, co
       }
     } else st8_f16x2(out + (size_t)m * out_cpitch + out_coff + c, out_ps, v, sat);
   }
-  if (sat && sat_flag) atomicOr(sat_flag, 1);
+  if (sat && sat_flag) atomicOr(sat_flag, YOLO_SAT_ACT_BN);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -414,7 +414,7 @@ bn_bwd_apply_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, 
       st8_f16x2(dzd + pix * C + c, dzd_ps, o, sat);
     }
   }
-  if (sat && sat_flag) atomicOr(sat_flag, 1);
+  if (sat && sat_flag) atomicOr(sat_flag, YOLO_SAT_GRAD);
 }
 
 // column sums of a dense fp32 [M][C] matrix (bias gradient of the head convs): one block per 32 channels, fixed order

@@ -242,7 +242,7 @@ __global__ void split_f16x2_kernel(const float* __restrict__ src, long long rows
     dst[i] = h;
     dst[plane_stride + i] = __float2half_rn(v - __half2float(h));
   }
-  if (sat && sat_flag) atomicOr(sat_flag, 1);
+  if (sat && sat_flag) atomicOr(sat_flag, YOLO_SAT_ACT_BN);
 }
 
 int launch_split_f16x2(const float* src, long long rows, int cols, int src_pitch, float scale, const float* scale_dev, void* dst, int dst_pitch,
