@@ -94,6 +94,7 @@ struct TrainLayer {                       // per conv op
   double* slab = nullptr;                             // [kStatSlabs][2][Cout] second-level partials (forward and backward)
   float* mean = nullptr; float* rstd = nullptr; float* rmean = nullptr; float* rvar = nullptr;
   // backward
+  float* ab = nullptr;                                // [2][Cout]: a = gamma*rstd, b = beta - mean*a  (u = a*z + b)
   float* mg = nullptr;                                // [2][Cout]: mean g, mean g*xhat
   float* dzscale = nullptr;                           // device: [0] = 2^s applied to dz, [1] = 2^-s, [2] = max|g| bits (uint)
   __half* dz = nullptr;  long long dz_plane_rows = 0; // scaled pre-activation gradient [2][dz_plane_rows][Cout]
@@ -208,7 +209,7 @@ reduce_groups_kernel(const float* __restrict__ part, size_t groups, int C, doubl
 }
 
 __global__ void bn_finalize_fwd_kernel(const double* __restrict__ slab, int nslab, int M, int C, float* mean, float* rstd, float* rmean, float* rvar,
-                                       float momentum) {
+                                       float momentum, const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ab) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s0 = 0.0, s1 = 0.0;
@@ -218,25 +219,32 @@ __global__ void bn_finalize_fwd_kernel(const double* __restrict__ slab, int nsla
   rstd[c] = (float)(1.0 / sqrt(var + (double)kTrainBnEps));
   rmean[c] = rmean[c] * momentum + (float)mu * (1.f - momentum);
   rvar[c] = rvar[c] * momentum + (float)var * (1.f - momentum);
+  const float a = gamma[c] * rstd[c];                        // u = gamma*(z - mean)*rstd + beta = a*z + b
+  ab[c] = a;
+  ab[C + c] = beta[c] - mean[c] * a;
 }
 
-// y = act(gamma * (z - mean) * rstd + beta) (+ residual), written through the op's output view (concat slice / 2x upsample)
+// y = act(a*z + b) (+ residual), written through the op's output view (concat slice / 2x upsample).  Block = (256 / octs) row lanes x
+// octs channel octets over <= 256 channels (per-channel constants live in registers); grid = (channel blocks, row blocks).
 __global__ void __launch_bounds__(256)
-bn_act_fwd_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
-                  const float* __restrict__ gamma, const float* __restrict__ beta, int act, const __half* __restrict__ res, int res_cpitch,
-                  int res_coff, long long res_ps, __half* __restrict__ out, int out_cpitch, int out_coff, long long out_ps, int upsample2,
-                  int Ho, int Wo, int* sat_flag) {
-  const int oct = C >> 3;
-  const size_t total = (size_t)M * oct;
+bn_act_fwd_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, const float* __restrict__ ab, int act,
+                  const __half* __restrict__ res, int res_cpitch, int res_coff, long long res_ps, __half* __restrict__ out, int out_cpitch,
+                  int out_coff, long long out_ps, int upsample2, int Ho, int Wo, int* sat_flag) {
+  const int cb = min(C, 256), octs = cb >> 3, lanes = 256 / octs;
+  const int oc = threadIdx.x % octs, rl = threadIdx.x / octs;
+  const int c = blockIdx.x * cb + oc * 8;
+  if (c >= C || rl >= lanes) return;
+  float a[8], b[8];
+  ld8_f32(ab + c, a);
+  ld8_f32(ab + C + c, b);
   int sat = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int m = (int)(i / oct), c = (int)(i - (size_t)m * oct) * 8;
+  for (int m = blockIdx.y * lanes + rl; m < M; m += gridDim.y * lanes) {
     float v[8], r[8];
     ld8_f16x2(z + (size_t)m * C + c, z_ps, v);
     if (res) ld8_f16x2(res + (size_t)m * res_cpitch + res_coff + c, res_ps, r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float u = fmaf((v[j] - mean[c + j]) * rstd[c + j], gamma[c + j], beta[c + j]);
+      float u = fmaf(v[j], a[j], b[j]);
       if (act == ACT_LEAKY) u = u > 0.f ? u : 0.1f * u;
       else if (act == ACT_RELU) u = fmaxf(u, 0.f);
       v[j] = res ? u + r[j] : u;
@@ -278,7 +286,7 @@ __device__ __forceinline__ void load_dy8(const float* dy, int dy_cpitch, int dy_
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, const float* __restrict__ dy, int dy_cpitch, int dy_coff,
                      int upsample2, int Ho, int Wo, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     const float* __restrict__ gamma, const float* __restrict__ beta, int act, float* __restrict__ dres, int dres_cpitch,
+                     const float* __restrict__ ab, int act, float* __restrict__ dres, int dres_cpitch,
                      int dres_coff, double* __restrict__ slab, unsigned int* __restrict__ gmax_bits) {
   const int cb = min(C, 256), octs = cb >> 3, lanes = 256 / octs;
   const int oc = threadIdx.x % octs, rl = threadIdx.x / octs;
@@ -292,7 +300,7 @@ bn_bwd_reduce_kernel(const __half* __restrict__ z, long long z_ps, int M, int C,
   if (c < C && rl < lanes) {
     float mu[8], rs[8], ga[8], be[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { mu[j] = mean[c + j]; rs[j] = rstd[c + j]; ga[j] = gamma[c + j]; be[j] = beta[c + j]; }
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[c + j]; rs[j] = rstd[c + j]; ga[j] = ab[c + j]; be[j] = ab[C + c + j]; }
     for (int mb = m0 + rl; mb < m1; mb += lanes * 16) {
       float f0[8], f1[8];
 #pragma unroll
@@ -312,7 +320,7 @@ bn_bwd_reduce_kernel(const __half* __restrict__ z, long long z_ps, int M, int C,
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (zv[j] - mu[j]) * rs[j];
-          const float gg = act_grad(g[j], fmaf(xh, ga[j], be[j]), act);
+          const float gg = act_grad(g[j], fmaf(zv[j], ga[j], be[j]), act);        // u = a*z + b exactly as the forward computed it
           f0[j] += gg; f1[j] = fmaf(gg, xh, f1[j]);
           gm = fmaxf(gm, fabsf(gg));
         }
@@ -379,19 +387,22 @@ bn_bwd_finalize_kernel(const double* __restrict__ slab, int nslab, int M, int C,
 }
 
 // dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)) * 2^s as fp16 planes (+ the zero-dilated copy for strided convolutions);
-// also zeroes the guard rows [M, M + kGuardRows) of dz.
+// also zeroes the guard rows [M, M + kGuardRows) of dz.  Thread mapping as in bn_act_fwd_kernel.
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, const float* __restrict__ mg, const float* __restrict__ dy,
                     int dy_cpitch, int dy_coff, int upsample2, int Ho, int Wo, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const float* __restrict__ gamma, const float* __restrict__ beta, int act, const float* __restrict__ dzscale,
+                    const float* __restrict__ ab, int act, const float* __restrict__ dzscale,
                     __half* __restrict__ dz, long long dz_ps, __half* __restrict__ dzd, long long dzd_ps, int stride, int Hin, int Win,
                     int* sat_flag) {
-  const int oct = C >> 3;
-  const size_t total = (size_t)(M + kGuardRows) * oct;
+  const int cb = min(C, 256), octs = cb >> 3, lanes = 256 / octs;
+  const int oc = threadIdx.x % octs, rl = threadIdx.x / octs;
+  const int c = blockIdx.x * cb + oc * 8;
+  if (c >= C || rl >= lanes) return;
   const float s = dzscale[0];
+  float mu[8], rs[8], a[8], b[8], m0[8], m1[8];
+  ld8_f32(mean + c, mu); ld8_f32(rstd + c, rs); ld8_f32(ab + c, a); ld8_f32(ab + C + c, b); ld8_f32(mg + c, m0); ld8_f32(mg + C + c, m1);
   int sat = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int m = (int)(i / oct), c = (int)(i - (size_t)m * oct) * 8;
+  for (int m = blockIdx.y * lanes + rl; m < M + kGuardRows; m += gridDim.y * lanes) {
     float o[8];
     if (m < M) {
       float zv[8], g[8];
@@ -399,9 +410,9 @@ bn_bwd_apply_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, 
       load_dy8(dy, dy_cpitch, dy_coff, upsample2, Ho, Wo, m, c, g);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float xh = (zv[j] - mean[c + j]) * rstd[c + j];
-        const float gg = act_grad(g[j], fmaf(xh, gamma[c + j], beta[c + j]), act);
-        o[j] = gamma[c + j] * rstd[c + j] * (gg - mg[c + j] - xh * mg[C + c + j]) * s;
+        const float xh = (zv[j] - mu[j]) * rs[j];
+        const float gg = act_grad(g[j], fmaf(zv[j], a[j], b[j]), act);
+        o[j] = a[j] * (gg - m0[j] - xh * m1[j]) * s;                  // a = gamma * rstd
       }
     } else {
 #pragma unroll
@@ -611,6 +622,11 @@ void train_release(yolo_handle* h, bool writeback) {
   h->train = nullptr;
 }
 
+// slabs of the FFMA weight-gradient kernel: split the pixel range until ~4 CTAs per SM exist
+static inline int simt_wgrad_slabs(int M, int K, int cout_pad) {
+  const int tiles = ((K + 63) / 64) * ((cout_pad + 63) / 64);
+  return std::max(1, std::min(M / 256, std::max(1, 592 / tiles)));
+}
 static inline int grad_pitch(const View& v) { return v.il ? v.cpitch / 2 : v.cpitch; }
 static float* grad_ptr(const yolo_handle* h, const View& v) {
   return reinterpret_cast<float*>(h->train->arena + h->train->gbuf_off[v.buf]);
@@ -691,7 +707,7 @@ extern "C" int yolo_train_init(yolo_handle* h, float* params_flat, float* grads_
     flat = (flat + 3) & ~(size_t)3;
     const size_t Mmax = (size_t)B * L.Ho * L.Wo;
     L.stat_groups = umma_stats_groups((int)Mmax);
-    tmp[i].small = take((size_t)(4 + 2 + 4) * op.cout * 4);                    // mean, rstd, rmean, rvar | mg[2] | dzscale (padded)
+    tmp[i].small = take((size_t)(4 + 2 + 2 + 4) * op.cout * 4);                // mean, rstd, rmean, rvar | mg[2] | ab[2] | dzscale (padded)
     tmp[i].slab = take((size_t)kStatSlabs * 2 * op.cout * 8);
     if (L.has_bn) {
       if (op.out.buf < 0) return hfail(h, fail(YOLO_E_UNSUPPORTED, "train_init: BatchNorm layer writing a user output"));
@@ -741,7 +757,7 @@ extern "C" int yolo_train_init(yolo_handle* h, float* params_flat, float* grads_
     const TrainLayer& L = T->layers[i];
     const size_t kn = (size_t)op.kh * op.kw * op.in.C * op.cout_pad * 4;
     const size_t Mmax = (size_t)B * L.Ho * L.Wo;
-    size_t need = kn * std::max<size_t>(1, std::min<size_t>(Mmax / 512, 64));                       // FFMA slabs (upper bound used by the launcher)
+    size_t need = kn * (size_t)simt_wgrad_slabs((int)Mmax, op.kh * op.kw * op.in.C, op.cout_pad);     // FFMA slabs (the launcher's formula at max batch)
     if (L.has_bn && op.in.buf >= 0 && wgrad_umma_eligible(op.in.C, op.cout, op.kh, op.kw, op.in.dtype, op.in.il)) {
       const int n_units = op.kh * op.kw * (op.in.C / 64), bn = op.cout % 256 == 0 ? 256 : (op.cout % 128 == 0 ? 128 : 64);
       const int tiles = ((n_units + 1) / 2) * (op.cout / bn);
@@ -786,7 +802,7 @@ extern "C" int yolo_train_init(yolo_handle* h, float* params_flat, float* grads_
     if (L.has_bias) memcpy(&hostP[L.o_bias], h->params[op.p_bias].host.data(), cout * 4);
     float* small = reinterpret_cast<float*>(T->arena + tmp[i].small);
     L.mean = small; L.rstd = small + cout; L.rmean = small + 2 * cout; L.rvar = small + 3 * cout;
-    L.mg = small + 4 * cout; L.dzscale = small + 6 * cout;
+    L.mg = small + 4 * cout; L.ab = small + 6 * cout; L.dzscale = small + 8 * cout;
     L.slab = reinterpret_cast<double*>(T->arena + tmp[i].slab);
     if (L.has_bn) {
       L.z = reinterpret_cast<__half*>(T->arena + tmp[i].z);
@@ -924,11 +940,16 @@ extern "C" int yolo_train_forward_backward(yolo_handle* h, const void* input, in
     }
     const int nslab = (int)std::max<size_t>(1, std::min<size_t>(kStatSlabs, groups / 64));
     reduce_groups_kernel<<<dim3((C + 31) / 32, nslab), 256, 0, st>>>(L.stat_part, groups, C, L.slab);
-    bn_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(L.slab, nslab, M, C, L.mean, L.rstd, L.rmean, L.rvar, T->bn_momentum);
+    bn_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(L.slab, nslab, M, C, L.mean, L.rstd, L.rmean, L.rvar, T->bn_momentum, T->P + L.o_gamma,
+                                                            T->P + L.o_beta, L.ab);
     const __half* res = op.has_res ? act16(h, op.res) : nullptr;
-    bn_act_fwd_kernel<<<grid_for((size_t)M * (C / 8), 256, 148 * 16), 256, 0, st>>>(
-        L.z, L.z_ps, M, C, L.mean, L.rstd, T->P + L.o_gamma, T->P + L.o_beta, op.act, res, op.res.cpitch, op.res.coff, op.res.ps, act16(h, op.out),
-        op.out.cpitch, op.out.coff, op.out.ps, op.upsample2, L.Ho, L.Wo, h->d_flags);
+    {
+      const int cb = std::min(C, 256), lanes = 256 / (cb / 8);
+      const int rowblocks = std::max(1, std::min((M + lanes - 1) / lanes, 148 * 8 / ((C + cb - 1) / cb)));
+      bn_act_fwd_kernel<<<dim3((C + cb - 1) / cb, rowblocks), 256, 0, st>>>(L.z, L.z_ps, M, C, L.ab, op.act, res, op.res.cpitch, op.res.coff, op.res.ps,
+                                                                          act16(h, op.out), op.out.cpitch, op.out.coff, op.out.ps, op.upsample2, L.Ho,
+                                                                          L.Wo, h->d_flags);
+    }
     g_launches += 3;
   }
   YB_CUDA(cudaGetLastError());
@@ -969,20 +990,23 @@ extern "C" int yolo_train_forward_backward(yolo_handle* h, const void* input, in
       const int cb = std::min(C, 256);
       const int nslab = std::max(1, std::min(kStatSlabs, M / 256));
       bn_bwd_reduce_kernel<<<dim3((C + cb - 1) / cb, nslab), 256, 0, st>>>(L.z, L.z_ps, M, C, dy, dyp, op.out.coff, op.upsample2, L.Ho, L.Wo, L.mean,
-                                                                         L.rstd, T->P + L.o_gamma, T->P + L.o_beta, op.act, dres,
-                                                                         op.has_res ? grad_pitch(op.res) : 0, op.res.coff, L.slab,
-                                                                         reinterpret_cast<unsigned int*>(L.dzscale + 2));
+                                                                         L.rstd, L.ab, op.act, dres, op.has_res ? grad_pitch(op.res) : 0, op.res.coff,
+                                                                         L.slab, reinterpret_cast<unsigned int*>(L.dzscale + 2));
       bn_bwd_finalize_kernel<<<1, 256, 0, st>>>(L.slab, nslab, M, C, T->P + L.o_gamma, L.rstd, L.mg, T->G + L.o_gamma, T->G + L.o_beta, L.dzscale);
-      bn_bwd_apply_kernel<<<grid_for((size_t)(M + kGuardRows) * (C / 8), 256, 148 * 16), 256, 0, st>>>(
-          L.z, L.z_ps, M, C, L.mg, dy, dyp, op.out.coff, op.upsample2, L.Ho, L.Wo, L.mean, L.rstd, T->P + L.o_gamma, T->P + L.o_beta, op.act, L.dzscale,
-          L.dz, L.dz_plane_rows * C, L.dzd, L.dzd_plane_rows * C, op.stride, op.in.H, op.in.W, h->d_flags);
+      {
+        const int lanes = 256 / (cb / 8);
+        const int rowblocks = std::max(1, std::min((M + kGuardRows + lanes - 1) / lanes, 148 * 8 / ((C + cb - 1) / cb)));
+        bn_bwd_apply_kernel<<<dim3((C + cb - 1) / cb, rowblocks), 256, 0, st>>>(
+            L.z, L.z_ps, M, C, L.mg, dy, dyp, op.out.coff, op.upsample2, L.Ho, L.Wo, L.mean, L.rstd, L.ab, op.act, L.dzscale, L.dz, L.dz_plane_rows * C,
+            L.dzd, L.dzd_plane_rows * C, op.stride, op.in.H, op.in.W, h->d_flags);
+      }
       g_launches += 3;
       // weight gradient
       if (L.wg.enabled) {
         rc = launch_wgrad_umma(L.wg, batch, T->G + L.o_w, op.cout_pad, 1.f, L.dzscale + 1, T->wg_scratch, T->wg_scratch_bytes, 0, st);
         if (rc) return hfail(h, rc);
       } else {
-        const int slabs = std::max(1, std::min(M / 512, 64));
+        const int slabs = simt_wgrad_slabs(M, K, op.cout_pad);
         const size_t kn = (size_t)K * op.cout_pad;
         dim3 gw((K + 63) / 64, (op.cout_pad + 63) / 64, slabs);
         const void* xin = op.in.buf == -1 ? input : (const void*)act16(h, op.in);
@@ -1021,7 +1045,7 @@ extern "C" int yolo_train_forward_backward(yolo_handle* h, const void* input, in
       // head conv (no BatchNorm, 90 / 10 channels): fp32 FFMA kernels on dz = d loss / d head
       float* dz = T->dheads[-2 - op.out.buf];
       if (L.has_bias) colsum_kernel<<<(C + 31) / 32, 256, 0, st>>>(dz, M, C, T->G + L.o_bias);
-      const int slabs = std::max(1, std::min(M / 512, 64));
+      const int slabs = simt_wgrad_slabs(M, K, op.cout_pad);
       const size_t kn = (size_t)K * op.cout_pad;
       dim3 gw((K + 63) / 64, (op.cout_pad + 63) / 64, slabs);
       wgrad_simt_kernel<true, false><<<gw, 256, 0, st>>>(act16(h, op.in), op.in.ps, batch, op.in.H, op.in.W, op.in.C, op.in.cpitch, op.in.coff, 0, dz, 0, C,
