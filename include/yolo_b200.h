@@ -192,6 +192,19 @@ int  yolo_loss_targets(const yolo_decode_geom* g, const void* const* heads, cons
                        const yolo_loss_params* p, void* scratch, float* out_losses, void* const* dheads, int32_t* out_assign,
                        void* stream);
 
+/* Licence-plate pose head: targets + the five LP losses (+ gradient of their sum w.r.t. the map) - `_find_best_LP`, `_loss_mask_LP`,
+ * `_get_loss_LP` (licence_plate/LP_detection.py:259-313,354-360; `_score_weight_LP` car_and_LP/YOLO.py:124-131).
+ * lp_map: device fp32 (B,hs,ws,ch) NHWC (nchw = 0, CarLPNet) or (B,ch,hs,ws) (nchw = 1, LPDenseNet); channels [score, x, y, z, r1, r2, r3, class...].
+ * labels: device fp32 (B, n_obj, n_lab >= 10) rows [flag (<0: none), X, Y, Z (mm), r1, r2, r3 (rad), pixel x, pixel y, ..., class index (last)].
+ * step: pixels per cell (2^num_downsample).  out_losses: device (5,B) = LP_score, LP_xy, LP_z, LP_r, LP_class.  dlp: NULL or like lp_map. */
+typedef struct yolo_lp_loss_params {
+  float scale_score, scale_xy, scale_z, scale_r, scale_class;   /* spec `scale` LP_* entries */
+  float positive_weight, negative_weight;                       /* LP_positive_weight, LP_negative_weight */
+} yolo_lp_loss_params;
+int  yolo_lp_loss_targets(const float* lp_map, int nchw, int batch, int hs, int ws, int ch, int step, const float r_max[3],
+                          const float* labels, int n_obj, int n_lab, const yolo_lp_loss_params* p, float* out_losses, float* dlp,
+                          void* stream);
+
 /* Training step (CARNET / CARLPNET, YOLO_PREC_FP16X3 = fp32-grade arithmetic on the tensor cores), one process per GPU.  The four
  * flat buffers (parameters, gradients, Adam m, Adam v) are caller-owned device memory of yolo_train_flat_size() floats each.
  * BatchNorm statistics stay local to the GPU (car/YOLO.py:94-96).  Every reduction is fixed-order: a step is bit-reproducible.
@@ -213,6 +226,11 @@ int  yolo_nccl_unique_id(void* id128);
 int  yolo_train_comm_init(yolo_handle* h, const void* id128, int rank, int world, size_t bucket_bytes);
 int  yolo_train_forward_backward(yolo_handle* h, const void* input, int in_layout, const float* labels, int batch, int n_obj,
                                  const yolo_loss_params* lp, float* out_losses, void* stream);
+/* car_and_LP `_train_batch(bxs, car_bys, LP_bys)` (car_and_LP/YOLO.py:265-304), CARLPNET: the backward starts from the sum of the five car
+ * losses AND the five LP losses.  lp_labels (B, n_lp_obj, n_lp_lab) as in yolo_lp_loss_targets; out_losses: device (10,B), car rows first. */
+int  yolo_train_forward_backward_lp(yolo_handle* h, const void* input, int in_layout, const float* labels, int batch, int n_obj,
+                                    const yolo_loss_params* lp, const float* lp_labels, int n_lp_obj, int n_lp_lab,
+                                    const yolo_lp_loss_params* lpp, float* out_losses, void* stream);
 int  yolo_train_apply(yolo_handle* h, float lr, float beta1, float beta2, float eps, float rescale_grad, void* stream);
 /* Read a parameter / running statistic (want_grad = 0) or its gradient (want_grad = 1) back in yolo_load_param's layout. */
 int  yolo_get_param(yolo_handle* h, const char* name, float* host, size_t n_elems, int want_grad);

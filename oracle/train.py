@@ -189,7 +189,7 @@ TRAINABLE = ("weight", "gamma", "beta", "bias")
 
 
 def train_step(net, spec, params, x, labels, hp, lr=0.001, batch_size=None, adam=None, t=1, car_rotate=False,
-               beta1=0.9, beta2=0.999, eps=1e-8, dtype=torch.float32):
+               beta1=0.9, beta2=0.999, eps=1e-8, dtype=torch.float32, lp_labels=None, lp_hp=None):
     """Forward in train mode (batch-statistics BN, per device), targets, the five losses, ``sum(losses).backward()``,
     then ``trainer.step(batch_size)``: grad * (1/batch_size) -> MXNet ``adam_update`` with the bias-corrected lr
     (``lr * sqrt(1-beta2^t)/(1-beta1^t)``, epsilon outside the square root, wd 0).  Single device (the multi-context sum of
@@ -202,6 +202,10 @@ def train_step(net, spec, params, x, labels, hp, lr=0.001, batch_size=None, adam
     heads = out if net == "carnet" else out[0]
     targets, mask, assign = loss_mask(spec, labels)
     losses = get_loss(spec, heads, targets, mask, hp, car_rotate)
+    if lp_labels is not None:                                  # car_and_LP/YOLO.py:265-304: the LP losses join the backward
+        lp_x = out[1][0]
+        lt, lm = loss_mask_LP(spec, lp_labels, spec["size"][0] // lp_x.shape[1])
+        losses = tuple(losses) + tuple(get_loss_LP(spec, lp_x, lt, lm, lp_hp))
     sum(l.sum() for l in losses).backward()
     grads = {k: v.grad.numpy().copy() for k, v in tp.items() if v.requires_grad}
     adam = adam or {k: (np.zeros_like(g), np.zeros_like(g)) for k, g in grads.items()}

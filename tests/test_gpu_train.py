@@ -213,3 +213,56 @@ def test_train_step_dk53_416():
     assert net.saturated() == 0
     tr.step(B)
     assert net.launches > 300
+
+
+# ---- licence-plate pose losses (LP_detection.py:259-360) and the car_and_LP step (car_and_LP/YOLO.py:265-304) ----------------
+@pytest.mark.parametrize("nchw", [False, True])
+def test_lp_loss_targets_match_oracle(nchw):
+    import yolo_b200
+    spec = nets.spec_tiny(size=(64, 96), C=9, lp=True)
+    B, step = 5, 8
+    hs, ws = spec["size"][0] // step, spec["size"][1] // step
+    rng = np.random.default_rng(3)
+    lp = rng.standard_normal((B, hs, ws, 10)).astype(np.float32)
+    labels = train.synthetic_LP_labels(B, spec["size"], nobj=3, seed=8, p_box=0.8)
+    labels[1, 1] = labels[1, 0]; labels[1, 1, 1:7] *= 0.5; labels[1, 1, 9] = (labels[1, 0, 9] + 1) % 3      # two labels in one cell: pose overwritten, classes accumulate
+    labels[2, 0, 7:9] = [1e4, -5.0]                                                                        # pixel outside the image: clipped
+    hp = dict(train.LP_V1_HPARAMS, scale=dict(train.LP_V1_HPARAMS["scale"], LP_class=0.3))
+    t, m = train.loss_mask_LP(spec, labels, step)
+    x = torch.from_numpy(lp).requires_grad_(True)
+    ol = train.get_loss_LP(spec, x, t, m, hp)
+    sum(l.sum() for l in ol).backward()
+    dev_map = torch.from_numpy(lp.transpose(0, 3, 1, 2).copy() if nchw else lp).cuda()
+    losses, dlp = yolo_b200.lp_loss_targets(dev_map, labels, step, spec["LP_r_max"], hp["scale"], hp["LP_positive_weight"], hp["LP_negative_weight"],
+                                            nchw=nchw, with_grad=True)
+    np.testing.assert_allclose(losses.cpu().numpy(), np.stack([l.detach().numpy() for l in ol]), rtol=2e-5, atol=1e-9)
+    g = dlp.cpu().numpy()
+    g = g.transpose(0, 2, 3, 1) if nchw else g
+    np.testing.assert_allclose(g, x.grad.numpy(), rtol=1e-4, atol=1e-9)
+
+
+def test_car_and_lp_train_step():
+    """CarLPNet: ten losses (five car + five LP) in one backward, against the oracle."""
+    import yolo_b200
+    spec = dict(spec_mid((64, 64), 10), LP_slice_point=[1, 3, 4, 7, 10], LP_r_max=[45, 60, 45], LP_num_class=3)
+    B = 2
+    params = weights.make_params("carlpnet", spec, seed=4, calib_batch=2)
+    x, _ = weights.synthetic_frames(B, spec["size"], seed=5)
+    labels = train.synthetic_labels(B, 4, nobj=2, seed=6, p_box=0.9)
+    lp_labels = train.synthetic_LP_labels(B, spec["size"], nobj=1, seed=7, p_box=1.0)
+    hp, lhp = train.V1_HPARAMS, dict(train.LP_V1_HPARAMS, scale=dict(train.LP_V1_HPARAMS["scale"], LP_class=0.3))
+    ref = train.train_step("carlpnet", spec, params, x, labels, hp, batch_size=B, lp_labels=lp_labels, lp_hp=lhp)
+    ref64 = train.train_step("carlpnet", spec, params, x, labels, hp, batch_size=B, lp_labels=lp_labels, lp_hp=lhp, dtype=torch.float64)
+    yspec = dict(spec, classes=[0, 1, 2, 3], batch_size=B, learning_rate=0.001, positive_weight=hp["positive_weight"], negative_weight=hp["negative_weight"],
+                 scale=dict(hp["scale"], **lhp["scale"]), LP_positive_weight=lhp["LP_positive_weight"], LP_negative_weight=lhp["LP_negative_weight"])
+    y = yolo_b200.CarLPYOLO(spec=yspec, params=params, precision="fp16x3", max_batch=B)
+    y._init_train()
+    xs = torch.from_numpy(x).cuda()
+    losses = y.trainer.forward_backward(xs, labels, y.scale, y.positive_weight, y.negative_weight, lp_labels=lp_labels,
+                                        lp_positive_weight=y.LP_positive_weight, lp_negative_weight=y.LP_negative_weight)
+    assert losses.shape == (10, B)
+    np.testing.assert_allclose(losses.cpu().numpy(), ref["losses"], rtol=2e-4, atol=1e-8)
+    worst = _grad_check(y.trainer, dict(y.net.param_shapes()), ref, ref64)
+    print(f"car_and_LP worst gradient rel L2 error {worst[0]:.2e} ({worst[1]})")
+    assert np.abs(y.trainer.get_param("LP_branch.5.weight", dict(y.net.param_shapes())["LP_branch.5.weight"], grad=True)).max() > 0
+    assert y._train_batch([xs], [labels], [lp_labels]) is None and y.backward_counter == 1 and y.last_losses.shape == (10, B)

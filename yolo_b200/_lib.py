@@ -46,6 +46,11 @@ class LossParams(C.Structure):
                 ("scale_class", C.c_float), ("positive_weight", C.c_float), ("negative_weight", C.c_float), ("car_rotate", C.c_int32)]
 
 
+class LpLossParams(C.Structure):
+    _fields_ = [("scale_score", C.c_float), ("scale_xy", C.c_float), ("scale_z", C.c_float), ("scale_r", C.c_float), ("scale_class", C.c_float),
+                ("positive_weight", C.c_float), ("negative_weight", C.c_float)]
+
+
 class NmsParams(C.Structure):
     _fields_ = [("score_thr", C.c_float), ("iou_thr", C.c_float), ("max_out", C.c_int32), ("max_cand", C.c_int32)]
 
@@ -74,6 +79,8 @@ SYMBOLS = {
     "yolo_decode_lp": (_I, [_VP, _I, _I, _I, _I, _I, C.POINTER(C.c_float * 3), _VP, _VP, _VP]),
     "yolo_loss_scratch_bytes": (_SZ, [_I, _I]),
     "yolo_loss_targets": (_I, [C.POINTER(DecodeGeom), C.POINTER(_VP), _VP, _I, _I, C.POINTER(LossParams), _VP, _VP, C.POINTER(_VP), _VP, _VP]),
+    "yolo_lp_loss_targets": (_I, [_VP, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_float * 3), _VP, _I, _I, C.POINTER(LpLossParams), _VP, _VP, _VP]),
+    "yolo_train_forward_backward_lp": (_I, [_VP, _VP, _I, _VP, _I, _I, C.POINTER(LossParams), _VP, _I, _I, C.POINTER(LpLossParams), _VP, _VP]),
     "yolo_train_flat_size": (_SZ, [_VP]),
     "yolo_train_init": (_I, [_VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "yolo_train_set_bn_momentum": (_I, [_VP, C.c_float]),

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (DecodeGeom, LossParams, NmsParams, YoloSpec, check, IN_NCHW_F32, IN_NHWC_U8, NET_CARNET, NET_CARLPNET,
+from ._lib import (DecodeGeom, LossParams, LpLossParams, NmsParams, YoloSpec, check, IN_NCHW_F32, IN_NHWC_U8, NET_CARNET, NET_CARLPNET,
                    NET_LPDENSENET, NET_DEBUGCONV, PRECISIONS)
 
 NET_TYPES = {"carnet": NET_CARNET, "carlpnet": NET_CARLPNET, "lpdensenet": NET_LPDENSENET, "debugconv": NET_DEBUGCONV}
@@ -349,6 +349,35 @@ def loss_targets(spec, heads, labels, scale, positive_weight, negative_weight, c
     return losses, assign, dheads
 
 
+def _lp_params(scale, positive_weight, negative_weight):
+    return LpLossParams(float(scale["LP_score"]), float(scale["LP_xy"]), float(scale["LP_z"]), float(scale["LP_r"]), float(scale["LP_class"]),
+                        float(positive_weight), float(negative_weight))
+
+
+def lp_loss_targets(lp_map, labels, step, r_max, scale, positive_weight, negative_weight, nchw=False, with_grad=False):
+    """`_loss_mask_LP` + `_get_loss_LP` (licence_plate/LP_detection.py:285-313,354-360) on the GPU.
+    lp_map: (B,Hs,Ws,ch) cuda fp32 (``nchw=False``, CarLPNet) or (B,ch,Hs,Ws) (LPDenseNet output); labels: (B,n_obj,>=10).
+    Returns (losses (5,B) cuda fp32 in order LP_score, LP_xy, LP_z, LP_r, LP_class, d(sum)/d(lp_map) or None)."""
+    lib = _lib.load()
+    t = _as_tensor(lp_map)
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4):
+        raise ValueError("lp_map must be a contiguous 4-d float32 CUDA tensor")
+    B = t.shape[0]
+    ch, hs, ws = (t.shape[1], t.shape[2], t.shape[3]) if nchw else (t.shape[3], t.shape[1], t.shape[2])
+    lab = torch.as_tensor(labels, dtype=torch.float32).to(t.device).contiguous()
+    if lab.dim() != 3 or lab.shape[0] != B or lab.shape[2] < 10:
+        raise ValueError(f"LP labels must be (B, n_obj, >= 10), got {tuple(lab.shape)}")
+    rm = (C.c_float * 3)(*[float(v) for v in r_max])
+    p = _lp_params(scale, positive_weight, negative_weight)
+    losses = torch.empty((5, B), dtype=torch.float32, device=t.device)
+    dlp = torch.empty_like(t) if with_grad else None
+    with torch.cuda.device(t.device):
+        check(lib.yolo_lp_loss_targets(C.c_void_p(t.data_ptr()), int(bool(nchw)), B, hs, ws, ch, int(step), C.byref(rm), C.c_void_p(lab.data_ptr()),
+                                       lab.shape[1], lab.shape[2], C.byref(p), C.c_void_p(losses.data_ptr()),
+                                       C.c_void_p(dlp.data_ptr()) if with_grad else None, _stream_ptr(t.device)))
+    return losses, dlp
+
+
 class Trainer:
     """Data-parallel training of a ``Net`` (CARNET / CARLPNET, precision fp16x3 = fp32-grade on the tensor cores), one process per
     GPU - the B200 shape of ``_init_train`` + ``_train_batch`` + ``gluon.Trainer(..., 'adam').step(batch_size)``
@@ -392,8 +421,10 @@ class Trainer:
     def set_bn_momentum(self, momentum):
         check(self.lib.yolo_train_set_bn_momentum(self.net._h, float(momentum)), self.net._h)
 
-    def forward_backward(self, images, labels, scale, positive_weight, negative_weight, car_rotate=False):
-        """images: (b,3,H,W) fp32 or (b,H,W,3) uint8; labels: (b,n_obj,6+num_class).  Returns the (5,b) losses (cuda).
+    def forward_backward(self, images, labels, scale, positive_weight, negative_weight, car_rotate=False, lp_labels=None,
+                         lp_positive_weight=1.0, lp_negative_weight=0.1):
+        """images: (b,3,H,W) fp32 or (b,H,W,3) uint8; labels: (b,n_obj,6+num_class).  Returns the (5,b) losses (cuda); with
+        ``lp_labels`` (b,n_lp,>=10) on a CarLPNet the five LP losses join the backward and (10,b) is returned (car rows first).
         With the library's communicator joined the gradient buffer holds the sum over ranks when this stream reaches it."""
         net = self.net
         x = net._to_device(images).contiguous()
@@ -402,11 +433,20 @@ class Trainer:
         B, n_obj = x.shape[0], lab.shape[1]
         p = LossParams(float(scale["score"]), float(scale["box_yx"]), float(scale["box_hw"]), float(scale["rotate"]), float(scale["class"]),
                        float(positive_weight), float(negative_weight), int(bool(car_rotate)))
-        losses = torch.empty((5, B), dtype=torch.float32, device=net.device)
         with torch.cuda.device(net.device):
-            check(self.lib.yolo_train_forward_backward(net._h, C.c_void_p(x.data_ptr()), layout, C.c_void_p(lab.data_ptr()), B, n_obj, C.byref(p),
-                                                       C.c_void_p(losses.data_ptr()), _stream_ptr(net.device)), net._h)
-        self._keep = (x, lab)
+            if lp_labels is None:
+                losses = torch.empty((5, B), dtype=torch.float32, device=net.device)
+                check(self.lib.yolo_train_forward_backward(net._h, C.c_void_p(x.data_ptr()), layout, C.c_void_p(lab.data_ptr()), B, n_obj, C.byref(p),
+                                                           C.c_void_p(losses.data_ptr()), _stream_ptr(net.device)), net._h)
+                self._keep = (x, lab)
+            else:
+                lpl = torch.as_tensor(lp_labels, dtype=torch.float32).to(net.device).contiguous()
+                lpp = _lp_params(scale, lp_positive_weight, lp_negative_weight)
+                losses = torch.empty((10, B), dtype=torch.float32, device=net.device)
+                check(self.lib.yolo_train_forward_backward_lp(net._h, C.c_void_p(x.data_ptr()), layout, C.c_void_p(lab.data_ptr()), B, n_obj, C.byref(p),
+                                                              C.c_void_p(lpl.data_ptr()), lpl.shape[1], lpl.shape[2], C.byref(lpp),
+                                                              C.c_void_p(losses.data_ptr()), _stream_ptr(net.device)), net._h)
+                self._keep = (x, lab, lpl)
         return losses
 
     def allreduce_grads(self):

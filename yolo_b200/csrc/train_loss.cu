@@ -221,6 +221,111 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partial, int chun
   losses[(size_t)q * B + b] = v / denom;
 }
 
+
+// ---- licence-plate pose head: targets + losses + head gradient (LP_detection.py:259-313,354-360; car_and_LP/YOLO.py:124-131) ----------
+// One CTA per image.  Labels: rows [flag, X, Y, Z (mm), r1, r2, r3 (rad), pixel x, pixel y, ..., class]; the target cell is
+// (clip(int(L[8] / step)), clip(int(L[7] / step))) - `_find_best_LP`; a later label overwrites the pose of an earlier one in the same
+// cell while the class one-hots accumulate (`_loss_mask_LP` never clears them).  Losses like the car head: LogisticLoss(binary) on the
+// score with where(mask, pos, neg) weights, HuberLoss on xy / z / r, SoftmaxCrossEntropy on the class logits, each the mean over the
+// non-batch axes.  The map is (B, Hs, Ws, ch) NHWC (car_and_LP) or (B, ch, Hs, Ws) NCHW (LPDenseNet output before `slice_out`).
+struct LpLossDev {
+  float s_score, s_xy, s_z, s_r, s_cls, w_pos, w_neg;
+  int n_obj, n_lab, n_class, hs, ws, ch, nchw;
+  float step, rmax[3];
+};
+struct LpRec { int cell; float t[6]; int cls; };
+
+__global__ void __launch_bounds__(kLossThreads)
+lp_loss_kernel(const float* __restrict__ lp, const float* __restrict__ labels, const LpLossDev p, float* __restrict__ losses, int B,
+               float* __restrict__ dlp) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ LpRec s_rec[kMaxObj];
+  __shared__ float s_red[kLossThreads / 32][5];
+  if (tid < p.n_obj) {
+    const float* L = labels + ((size_t)b * p.n_obj + tid) * p.n_lab;
+    LpRec r;
+    r.cell = -1; r.cls = -1;
+    if (L[0] >= 0.f) {
+      int hf = (int)__fdiv_rn(L[8], p.step), wf = (int)__fdiv_rn(L[7], p.step);          // int(): truncation toward zero
+      hf = min(max(hf, 0), p.hs - 1); wf = min(max(wf, 0), p.ws - 1);
+      r.cell = hf * p.ws + wf;
+      r.t[0] = __fdiv_rn(L[1], 1000.f); r.t[1] = __fdiv_rn(L[2], 1000.f); r.t[2] = __fdiv_rn(L[3], 1000.f);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float rm = __fdiv_rn(__fmul_rn(p.rmax[i], 3.14159265358979323846f), 180.f);
+        const float x = __fadd_rn(__fdiv_rn(__fdiv_rn(L[4 + i], rm), 2.f), 0.5f);
+        r.t[3 + i] = -logf(__fsub_rn(__fdiv_rn(1.f, x), 1.f));                            // nd_inv_sigmoid (yolo_gluon.py:365-367)
+      }
+      const int c = (int)L[p.n_lab - 1];
+      r.cls = (c >= 0 && c < p.n_class) ? c : -1;
+    }
+    s_rec[tid] = r;
+  }
+  __syncthreads();
+  const int cells = p.hs * p.ws;
+  const float N = (float)cells;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = tid; k < cells; k += kLossThreads) {
+    int j = -1;
+    unsigned clsmask = 0;
+    for (int q = 0; q < p.n_obj; ++q)
+      if (s_rec[q].cell == k) { j = q; if (s_rec[q].cls >= 0) clsmask |= 1u << s_rec[q].cls; }
+    auto at = [&](int c) -> size_t { return p.nchw ? ((size_t)b * p.ch + c) * cells + k : ((size_t)b * cells + k) * p.ch + c; };
+    float v[32];
+    for (int c = 0; c < p.ch; ++c) v[c] = __ldg(lp + at(c));
+    const float l = j >= 0 ? 1.f : -1.f;
+    const float w = (j >= 0 ? p.w_pos : p.w_neg) * p.s_score;
+    const float pl = v[0] * l;
+    acc[0] += (fmaxf(-pl, 0.f) + softplus_neg_abs(pl)) * w;
+    if (dlp) {
+      dlp[at(0)] = w * (-l) / (1.f + expf(pl)) / N;
+      if (j < 0)
+        for (int c = 1; c < p.ch; ++c) dlp[at(c)] = 0.f;
+    }
+    if (j >= 0) {
+      const LpRec& r = s_rec[j];
+      const float d0 = v[1] - r.t[0], d1 = v[2] - r.t[1], d2 = v[3] - r.t[2], d3 = v[4] - r.t[3], d4 = v[5] - r.t[4], d5 = v[6] - r.t[5];
+      acc[1] += (huber(d0) + huber(d1)) * p.s_xy;
+      acc[2] += huber(d2) * p.s_z;
+      acc[3] += (huber(d3) + huber(d4) + huber(d5)) * p.s_r;
+      float mx = -CUDART_INF_F;
+      for (int c = 7; c < p.ch; ++c) mx = fmaxf(mx, v[c]);
+      float se = 0.f, sl = 0.f, dot = 0.f;
+      for (int c = 7; c < p.ch; ++c) {
+        const float lab = (clsmask >> (c - 7)) & 1u ? 1.f : 0.f;
+        se += expf(v[c] - mx); sl += lab; dot += (v[c] - mx) * lab;
+      }
+      if (p.ch > 7) acc[4] += (logf(se) * sl - dot) * p.s_cls;
+      if (dlp) {
+        dlp[at(1)] = p.s_xy * huber_grad(d0) / (2.f * N);
+        dlp[at(2)] = p.s_xy * huber_grad(d1) / (2.f * N);
+        dlp[at(3)] = p.s_z * huber_grad(d2) / N;
+        dlp[at(4)] = p.s_r * huber_grad(d3) / (3.f * N);
+        dlp[at(5)] = p.s_r * huber_grad(d4) / (3.f * N);
+        dlp[at(6)] = p.s_r * huber_grad(d5) / (3.f * N);
+        for (int c = 7; c < p.ch; ++c) {
+          const float lab = (clsmask >> (c - 7)) & 1u ? 1.f : 0.f;
+          dlp[at(c)] = p.s_cls * (expf(v[c] - mx) / se * sl - lab) / N;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    float x = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) s_red[warp][q] = x;
+  }
+  __syncthreads();
+  if (tid < 5) {
+    float x = 0.f;
+    for (int w2 = 0; w2 < kLossThreads / 32; ++w2) x += s_red[w2][tid];
+    const float denom = tid == 1 ? 2.f * N : (tid == 3 ? 3.f * N : N);
+    losses[(size_t)tid * B + b] = x / denom;
+  }
+}
+
 }  // namespace yb
 
 using namespace yb;
@@ -259,6 +364,25 @@ extern "C" int yolo_loss_targets(const yolo_decode_geom* g, const void* const* h
   loss_kernel<<<dim3(chunks, batch), kLossThreads, 0, st>>>(d, lp, labels, recs, partial, dh[0], dh[1], dh[2]);
   loss_finalize_kernel<<<(5 * batch + 127) / 128, 128, 0, st>>>(partial, chunks, batch, (float)d.total, out_losses);
   g_launches += 3;
+  YB_CUDA(cudaGetLastError());
+  return YOLO_OK;
+}
+
+extern "C" int yolo_lp_loss_targets(const float* lp_map, int nchw, int batch, int hs, int ws, int ch, int step, const float r_max[3],
+                                    const float* labels, int n_obj, int n_lab, const yolo_lp_loss_params* p, float* out_losses, float* dlp,
+                                    void* stream) {
+  if (!lp_map || !labels || !p || !out_losses || !r_max || batch < 0 || hs < 1 || ws < 1 || step < 1) return fail(YOLO_E_BADARG, "lp_loss_targets: bad arguments");
+  if (ch < 7 || ch > 32 || n_lab < 10 || n_obj < 1) return fail(YOLO_E_BADARG, "lp_loss_targets: ch=%d n_lab=%d n_obj=%d unsupported", ch, n_lab, n_obj);
+  if (n_obj > kMaxObj) return fail(YOLO_E_UNSUPPORTED, "lp_loss_targets: at most %d labels per image", kMaxObj);
+  if (batch == 0) return YOLO_OK;
+  LpLossDev d;
+  d.s_score = p->scale_score; d.s_xy = p->scale_xy; d.s_z = p->scale_z; d.s_r = p->scale_r; d.s_cls = p->scale_class;
+  d.w_pos = p->positive_weight; d.w_neg = p->negative_weight;
+  d.n_obj = n_obj; d.n_lab = n_lab; d.n_class = ch - 7; d.hs = hs; d.ws = ws; d.ch = ch; d.nchw = nchw ? 1 : 0;
+  d.step = (float)step;
+  for (int i = 0; i < 3; ++i) d.rmax[i] = r_max[i];
+  lp_loss_kernel<<<batch, kLossThreads, 0, (cudaStream_t)stream>>>(lp_map, labels, d, out_losses, batch, dlp);
+  ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
 }

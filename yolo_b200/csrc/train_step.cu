@@ -891,8 +891,8 @@ extern "C" int yolo_train_comm_init(yolo_handle* h, const void* id128, int rank,
 
 // forward (train-mode BN) + targets/losses + backward: fills the flat gradient buffer (d sum(losses) / d param); with a communicator
 // the gradient is all-reduced (sum over ranks) bucket by bucket while the backward runs.
-extern "C" int yolo_train_forward_backward(yolo_handle* h, const void* input, int in_layout, const float* labels, int batch, int n_obj,
-                                           const yolo_loss_params* lp, float* out_losses, void* stream) {
+static int train_fwd_bwd(yolo_handle* h, const void* input, int in_layout, const float* labels, int batch, int n_obj, const yolo_loss_params* lp,
+                         const float* lp_labels, int n_lp_obj, int n_lp_lab, const yolo_lp_loss_params* lpp, float* out_losses, void* stream) {
   if (!h || !h->train) return fail(YOLO_E_STATE, "train: yolo_train_init has not been called");
   if (!input || !labels || !lp || !out_losses) return hfail(h, fail(YOLO_E_BADARG, "train: null argument"));
   if (batch < 1 || batch > h->spec.max_batch) return hfail(h, fail(YOLO_E_SHAPE, "train: batch=%d outside [1,%d]", batch, h->spec.max_batch));
@@ -968,9 +968,14 @@ extern "C" int yolo_train_forward_backward(yolo_handle* h, const void* input, in
   for (int i = 0; i < s.n_scales; ++i) dheads[i] = T->dheads[i];
   rc = yolo_loss_targets(&g, heads, labels, batch, n_obj, lp, T->loss_scratch, out_losses, dheads, nullptr, stream);
   if (rc) return hfail(h, rc);
-  for (size_t i = s.n_scales; i < h->outputs.size(); ++i) {      // outputs without a loss in this step (the LP map of CARLPNET): zero gradient
+  for (size_t i = s.n_scales; i < h->outputs.size(); ++i) {
     const View& v = h->outputs[i];
-    YB_CUDA(cudaMemsetAsync(T->dheads[i], 0, (size_t)batch * v.H * v.W * v.C * 4, st));
+    if (lp_labels) {                                              // car_and_LP `_train_batch`: the five LP losses join the backward
+      rc = yolo_lp_loss_targets(static_cast<const float*>(heads[i]), 0, batch, v.H, v.W, v.C, s.height / v.H, s.lp_r_max, lp_labels, n_lp_obj, n_lp_lab,
+                                lpp, out_losses + (size_t)5 * batch, T->dheads[i], stream);
+      if (rc) return hfail(h, rc);
+    } else                                                        // car/YOLO.py `_train_batch` on a CarLPNet: no loss on the LP map, zero gradient
+      YB_CUDA(cudaMemsetAsync(T->dheads[i], 0, (size_t)batch * v.H * v.W * v.C * 4, st));
   }
   // ---------------- backward ----------------
   YB_CUDA(cudaMemsetAsync(T->arena + T->grads_begin, 0, T->grads_bytes, st));
@@ -1084,6 +1089,20 @@ extern "C" int yolo_train_forward_backward(yolo_handle* h, const void* input, in
   YB_CUDA(cudaGetLastError());
   h->last_launches = g_launches - launches0;
   return YOLO_OK;
+}
+
+extern "C" int yolo_train_forward_backward(yolo_handle* h, const void* input, int in_layout, const float* labels, int batch, int n_obj,
+                                           const yolo_loss_params* lp, float* out_losses, void* stream) {
+  return train_fwd_bwd(h, input, in_layout, labels, batch, n_obj, lp, nullptr, 0, 0, nullptr, out_losses, stream);
+}
+
+extern "C" int yolo_train_forward_backward_lp(yolo_handle* h, const void* input, int in_layout, const float* labels, int batch, int n_obj,
+                                              const yolo_loss_params* lp, const float* lp_labels, int n_lp_obj, int n_lp_lab,
+                                              const yolo_lp_loss_params* lpp, float* out_losses, void* stream) {
+  if (!h) return fail(YOLO_E_BADARG, "train: null handle");
+  if (h->spec.net_type != YOLO_NET_CARLPNET) return hfail(h, fail(YOLO_E_UNSUPPORTED, "train: LP losses need a CARLPNET"));
+  if (!lp_labels || !lpp) return hfail(h, fail(YOLO_E_BADARG, "train: null LP labels / parameters"));
+  return train_fwd_bwd(h, input, in_layout, labels, batch, n_obj, lp, lp_labels, n_lp_obj, n_lp_lab, lpp, out_losses, stream);
 }
 
 // trainer.step(batch_size): G holds the SUM over ranks (reduced during the backward when a communicator is attached, else by the

@@ -165,6 +165,26 @@ class CarLPYOLO(YOLO):
 
     net_type = "carlpnet"
 
+    def _train_batch(self, bxs, car_bys, LP_bys=None, car_rotate=False):
+        """car_and_LP/YOLO.py:265-304: forward, car targets + losses, LP targets + losses (`_loss_mask_LP`, `_score_weight_LP`,
+        `_get_loss_LP`), backward of the sum of all ten, ``trainer.step(batch_size)``.  One list entry per process (torchrun contract).
+        ``self.last_losses`` is (10,b): the five car losses then LP_score, LP_xy, LP_z, LP_r, LP_class.  Without ``LP_bys`` it is the
+        car-only step of car/YOLO.py:350-399."""
+        if LP_bys is None:
+            return YOLO._train_batch(self, bxs, car_bys, car_rotate)
+        if not hasattr(self, "trainer"):
+            self._init_train()
+        if len(bxs) != 1 or len(car_bys) != 1 or len(LP_bys) != 1:
+            raise ValueError("one process per GPU (torchrun contract, INTEGRATION.md): pass this rank's slice as single-element lists")
+        self.last_losses = self.trainer.forward_backward(bxs[0], car_bys[0], self.scale, self.positive_weight, self.negative_weight, car_rotate,
+                                                         lp_labels=LP_bys[0], lp_positive_weight=getattr(self, "LP_positive_weight", 1.0),
+                                                         lp_negative_weight=getattr(self, "LP_negative_weight", 0.1))
+        self.trainer.allreduce_grads()
+        self.trainer.step(self.global_batch_size)
+        self.backward_counter += 1
+
+    train_step = _train_batch
+
     def predict_LP(self, LP_batch_out, return_index=False):
         """car_and_LP/YOLO.py:133-157: [LP_x (B,Hs,Ws,10)] -> np.float32 (B,7)."""
         lp = LP_batch_out[0] if isinstance(LP_batch_out, (list, tuple)) else LP_batch_out
@@ -198,6 +218,15 @@ class LicencePlateDetectioin:
         if return_index:
             return rows[0], int(idx[0].item())
         return rows[0]
+
+    def _loss_mask_LP_and_get_loss(self, net_out, LP_by, with_grad=False):
+        """GPU replacement of ``_loss_mask_LP`` + ``_get_loss_LP`` (+ the score weights of ``_train_batch_LP``), LP_detection.py:285-360:
+        net_out = the NCHW (B,ch,H/32,W/32) network output, LP_by = labels (B,n_obj,>=10).  Returns the (5,B) losses (and the gradient of
+        their sum w.r.t. net_out).  The DenseNet's own backward is not part of this build (out of scope for round 2)."""
+        out = net_out[0] if isinstance(net_out, (list, tuple)) else net_out
+        losses, dlp = api.lp_loss_targets(out, LP_by, 2 ** self.num_downsample, self.LP_r_max, self.scale, self.LP_positive_weight,
+                                          self.LP_negative_weight, nchw=True, with_grad=with_grad)
+        return (losses, dlp) if with_grad else losses
 
     def predict_LP_batch(self, batch_out):
         """Same decode applied to every image of the batch -> (B,10) (extension for batched serving)."""
