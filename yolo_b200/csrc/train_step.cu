@@ -40,7 +40,7 @@ namespace yb {
 constexpr float kBnMomentum = 0.9f;       // gluon BatchNorm() default (TrainState::bn_momentum)
 constexpr float kTrainBnEps = 1e-5f;
 constexpr int kGuardRows = 128;           // zero rows behind the last pixel of dz (tiles of the tensor-core kernels run past M)
-constexpr int kStatSlabs = 32;            // second-level slabs of the fixed-order channel reductions
+constexpr int kSlabCtas = 592;             // CTAs a slab-reduction launch aims for (4 per SM)
 
 // ---- minimal NCCL binding, resolved at run time from the libnccl the process already has (torch's) -------------------------
 typedef struct ncclComm* ncclComm_t;
@@ -91,12 +91,12 @@ struct TrainLayer {                       // per conv op
   __half* z = nullptr;  long long z_ps = 0;          // raw conv output, fp16 planes [2][max_batch*Ho*Wo][Cout]
   float* zf = nullptr;                                // head convs: fp32 output (= the head tensor)
   float* stat_part = nullptr;  size_t stat_groups = 0;   // per-warp partial sums [groups][2][Cout]
-  double* slab = nullptr;                             // [kStatSlabs][2][Cout] second-level partials (forward and backward)
+  double* slab = nullptr;  int slab_cap = 1;          // [slab_cap][2][Cout] second-level partials (forward and backward)
   float* mean = nullptr; float* rstd = nullptr; float* rmean = nullptr; float* rvar = nullptr;
   // backward
   float* ab = nullptr;                                // [2][Cout]: a = gamma*rstd, b = beta - mean*a  (u = a*z + b)
   float* mg = nullptr;                                // [2][Cout]: mean g, mean g*xhat
-  float* dzscale = nullptr;                           // device: [0] = 2^s applied to dz, [1] = 2^-s, [2] = max|g| bits (uint)
+  float* dzscale = nullptr;                           // device: [0] = 2^s applied to dz, [1] = 2^-s, [2] = max|g| bits, [3] = max|gamma*rstd| bits (uint)
   __half* dz = nullptr;  long long dz_plane_rows = 0; // scaled pre-activation gradient [2][dz_plane_rows][Cout]
   __half* dzd = nullptr; long long dzd_plane_rows = 0; int dzd_n = 0;   // stride > 1: the same, zero-dilated to the input resolution
   UmmaConv dgrad;                                     // data-gradient convolution (Cout -> Cin, flipped filter)
@@ -208,12 +208,18 @@ reduce_groups_kernel(const float* __restrict__ part, size_t groups, int C, doubl
   }
 }
 
-__global__ void bn_finalize_fwd_kernel(const double* __restrict__ slab, int nslab, int M, int C, float* mean, float* rstd, float* rmean, float* rvar,
-                                       float momentum, const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ab) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// mean / rstd / running statistics / folded (a, b) from the slab partials: one warp per channel, lanes stride over the slabs,
+// shuffle tree (fixed order -> deterministic)
+__global__ void __launch_bounds__(256)
+bn_finalize_fwd_kernel(const double* __restrict__ slab, int nslab, int M, int C, float* mean, float* rstd, float* rmean, float* rvar,
+                       float momentum, const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ab) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s0 = 0.0, s1 = 0.0;
-  for (int y = 0; y < nslab; ++y) { s0 += slab[((size_t)y * 2) * C + c]; s1 += slab[((size_t)y * 2 + 1) * C + c]; }
+  for (int y = lane; y < nslab; y += 32) { s0 += slab[((size_t)y * 2) * C + c]; s1 += slab[((size_t)y * 2 + 1) * C + c]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, o); s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o); }
+  if (lane) return;
   const double mu = s0 / M, var = fmax(s1 / M - mu * mu, 0.0);
   mean[c] = (float)mu;
   rstd[c] = (float)(1.0 / sqrt(var + (double)kTrainBnEps));
@@ -329,14 +335,27 @@ bn_bwd_reduce_kernel(const __half* __restrict__ z, long long z_ps, int M, int C,
       for (int j = 0; j < 8; ++j) { s0[j] += f0[j]; s1[j] += f1[j]; }
     }
   }
-  // row lanes -> one value per channel (shared memory, fixed order)
+  // row lanes -> one value per channel (shared memory; binary tree when the lane count is a power of two - fixed order either way)
   __shared__ double sh[256][9];
+  const bool pow2 = (lanes & (lanes - 1)) == 0;
   for (int q = 0; q < 2; ++q) {
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = q == 0 ? s0[j] : s1[j];
     __syncthreads();
-    if (rl == 0 && c < C) {
+    if (pow2) {
+      for (int st = lanes >> 1; st >= 1; st >>= 1) {
+        if (rl < st) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] += sh[(rl + st) * octs + oc][j];
+        }
+        __syncthreads();
+      }
+      if (rl == 0 && c < C) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) slab[((size_t)blockIdx.y * 2 + q) * C + c + j] = sh[threadIdx.x][j];
+      }
+    } else if (rl == 0 && c < C) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         double a = 0.0;
@@ -354,36 +373,37 @@ bn_bwd_reduce_kernel(const __half* __restrict__ z, long long z_ps, int M, int C,
   if ((threadIdx.x & 31) == 0 && gm > 0.f) atomicMax(gmax_bits, __float_as_uint(gm));
 }
 
-// per channel: mean g, mean g*xhat, dgamma, dbeta; per layer: the power-of-two dz scale from the bound
-// |dz| <= max_c|gamma*rstd| * max|g| * 8 (|xhat| <= 6 assumed; the fp16 high plane still has 16x headroom and saturation is flagged)
+// per channel: mean g, mean g*xhat, dgamma, dbeta (one warp per channel, fixed-order shuffle tree) and the layer's max|gamma*rstd|
 __global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const double* __restrict__ slab, int nslab, int M, int C, const float* __restrict__ gamma, const float* __restrict__ rstd,
-                       float* __restrict__ mg, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dzscale) {
-  __shared__ float s_amax[256];
-  float amax = 0.f;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    double s0 = 0.0, s1 = 0.0;
-    for (int y = 0; y < nslab; ++y) { s0 += slab[((size_t)y * 2) * C + c]; s1 += slab[((size_t)y * 2 + 1) * C + c]; }
-    mg[c] = (float)(s0 / M); mg[C + c] = (float)(s1 / M);
-    dbeta[c] = (float)s0; dgamma[c] = (float)s1;
-    amax = fmaxf(amax, fabsf(gamma[c] * rstd[c]));
+bn_bwd_finalize_kernel(const double* __restrict__ slab, int nslab, int M, int C, const float* __restrict__ ab, float* __restrict__ mg,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, unsigned int* __restrict__ amax_bits) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int y = lane; y < nslab; y += 32) { s0 += slab[((size_t)y * 2) * C + c]; s1 += slab[((size_t)y * 2 + 1) * C + c]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, o); s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o); }
+  if (lane) return;
+  mg[c] = (float)(s0 / M); mg[C + c] = (float)(s1 / M);
+  dbeta[c] = (float)s0; dgamma[c] = (float)s1;
+  atomicMax(amax_bits, __float_as_uint(fabsf(ab[c])));        // order independent
+}
+
+// power-of-two dz scale from the bound |dz| <= max_c|gamma*rstd| * max|g| * 8 (|xhat| <= 6 assumed; the fp16 high plane still has
+// 16x headroom above the bound, and saturation is flagged)
+__device__ __forceinline__ float dz_scale_from(const float* dzscale) {
+  const float gmax = __uint_as_float(reinterpret_cast<const unsigned int*>(dzscale)[2]);
+  const float amax = __uint_as_float(reinterpret_cast<const unsigned int*>(dzscale)[3]);
+  const float bound = amax * gmax * 8.f;
+  float s = 1.f;
+  if (bound > 0.f && isfinite(bound)) {
+    int e;
+    frexpf(bound, &e);                                      // bound = f * 2^e, f in [0.5, 1)
+    int sh = 12 - e;
+    sh = sh < -100 ? -100 : (sh > 100 ? 100 : sh);
+    s = ldexpf(1.f, sh);
   }
-  s_amax[threadIdx.x] = amax;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 256; ++i) amax = fmaxf(amax, s_amax[i]);
-    const float gmax = __uint_as_float(reinterpret_cast<const unsigned int*>(dzscale)[2]);
-    const float bound = amax * gmax * 8.f;
-    float s = 1.f;
-    if (bound > 0.f && isfinite(bound)) {
-      int e;
-      frexpf(bound, &e);                                  // bound = f * 2^e, f in [0.5, 1)
-      int sh = 12 - e;
-      sh = sh < -100 ? -100 : (sh > 100 ? 100 : sh);
-      s = ldexpf(1.f, sh);
-    }
-    dzscale[0] = s; dzscale[1] = 1.f / s;
-  }
+  return s;
 }
 
 // dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)) * 2^s as fp16 planes (+ the zero-dilated copy for strided convolutions);
@@ -391,14 +411,15 @@ bn_bwd_finalize_kernel(const double* __restrict__ slab, int nslab, int M, int C,
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, const float* __restrict__ mg, const float* __restrict__ dy,
                     int dy_cpitch, int dy_coff, int upsample2, int Ho, int Wo, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const float* __restrict__ ab, int act, const float* __restrict__ dzscale,
+                    const float* __restrict__ ab, int act, float* __restrict__ dzscale,
                     __half* __restrict__ dz, long long dz_ps, __half* __restrict__ dzd, long long dzd_ps, int stride, int Hin, int Win,
                     int* sat_flag) {
   const int cb = min(C, 256), octs = cb >> 3, lanes = 256 / octs;
   const int oc = threadIdx.x % octs, rl = threadIdx.x / octs;
   const int c = blockIdx.x * cb + oc * 8;
   if (c >= C || rl >= lanes) return;
-  const float s = dzscale[0];
+  const float s = dz_scale_from(dzscale);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { dzscale[0] = s; dzscale[1] = 1.f / s; }   // read by the dgrad / wgrad epilogues
   float mu[8], rs[8], a[8], b[8], m0[8], m1[8];
   ld8_f32(mean + c, mu); ld8_f32(rstd + c, rs); ld8_f32(ab + c, a); ld8_f32(ab + C + c, b); ld8_f32(mg + c, m0); ld8_f32(mg + C + c, m1);
   int sat = 0;
@@ -428,20 +449,32 @@ bn_bwd_apply_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, 
   if (sat && sat_flag) atomicOr(sat_flag, YOLO_SAT_GRAD);
 }
 
-// column sums of a dense fp32 [M][C] matrix (bias gradient of the head convs): one block per 32 channels, fixed order
+// column sums of a dense fp32 [M][C] matrix (bias gradient of the head convs): slab partials (double) + a warp-per-channel finalize
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ a, int M, int C, float* __restrict__ out) {
+colsum_slab_kernel(const float* __restrict__ a, int M, int C, double* __restrict__ slab) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const int per = (M + gridDim.y - 1) / gridDim.y;
+  const int m0 = blockIdx.y * per, m1 = min(M, m0 + per);
   double s = 0.0;
   if (c < C)
-    for (int m = rl; m < M; m += 8) s += a[(size_t)m * C + c];
+    for (int m = m0 + rl; m < m1; m += 8) s += a[(size_t)m * C + c];
   __shared__ double sh[8][32];
   sh[rl][threadIdx.x & 31] = s;
   __syncthreads();
   if (rl == 0 && c < C) {
     for (int r = 1; r < 8; ++r) s += sh[r][threadIdx.x & 31];
-    out[c] = (float)s;
+    slab[(size_t)blockIdx.y * C + c] = s;
   }
+}
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(const double* __restrict__ slab, int nslab, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int y = lane; y < nslab; y += 32) s += slab[(size_t)y * C + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if (lane == 0) out[c] = (float)s;
 }
 
 // FFMA weight gradient for the shapes the tensor-core kernel does not take: dW[k][n] = sum_m A[m][k] * dz[m][n], A = im2col gather of
@@ -522,6 +555,60 @@ wgrad_simt_kernel(const void* __restrict__ xv, long long x_ps, int N, int H, int
       const int n = n0 + tn * 4 + j;
       if (n < cout_pad) op[(size_t)k * cout_pad + n] = n < Cout ? acc[i][j] : 0.f;
     }
+  }
+}
+// Weight gradient of the 3-channel stem (K = kh*kw*3 <= 32 rows, Cout <= 32): the 64 x 64 tile of wgrad_simt_kernel would be 80 % empty.
+// Each block owns a slab of pixels; per chunk of 64 pixels the im2col patch (coalesced along the image row) and the dz rows are staged
+// in shared memory and every thread accumulates its (k, n) outputs.  Slab partials are summed in a fixed order by wgrad_reduce_scaled.
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const void* __restrict__ xv, int in_layout, int N, int H, int W, const __half* __restrict__ dz, long long dz_ps, int Ho, int Wo,
+                  int Cout, int kh, int kw, int stride, int pad, float* __restrict__ part, size_t slab_stride, int cout_pad) {
+  constexpr int TM = 64, KMAX = 32, NMAX = 32;
+  __shared__ float xs[KMAX][TM + 1];
+  __shared__ float ds[TM][NMAX + 1];
+  const int K = kh * kw * 3, M = N * Ho * Wo, HoWo = Ho * Wo;
+  const int slabM = (M + gridDim.x - 1) / gridDim.x;
+  const int m_begin = blockIdx.x * slabM, m_end = min(M, m_begin + slabM);
+  const int tid = threadIdx.x;
+  const int npairs = K * Cout;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int pk[4], pn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const int idx = tid + 256 * i; pk[i] = idx < npairs ? idx / Cout : 0; pn[i] = idx < npairs ? idx % Cout : 0; }
+  for (int mb = m_begin; mb < m_end; mb += TM) {
+    for (int e = tid; e < K * TM; e += 256) {
+      const int k = e / TM, ml = e - k * TM, m = mb + ml;
+      float v = 0.f;
+      if (m < m_end) {
+        const int tap = k / 3, c = k - tap * 3, r = tap / kw, sx = tap - r * kw;
+        const int n = m / HoWo, rem = m - n * HoWo, oh = rem / Wo, ow = rem - oh * Wo;
+        const int ih = oh * stride - pad + r, iw = ow * stride - pad + sx;
+        if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
+          if (in_layout == 1) v = __ldg(static_cast<const float*>(xv) + ((size_t)(n * 3 + c) * H + ih) * W + iw);
+          else v = (float)__ldg(static_cast<const unsigned char*>(xv) + ((size_t)(n * H + ih) * W + iw) * 3 + c) / 255.f;
+        }
+      }
+      xs[k][ml] = v;
+    }
+    for (int e = tid; e < TM * Cout; e += 256) {
+      const int ml = e / Cout, n = e - ml * Cout, m = mb + ml;
+      float v = 0.f;
+      if (m < m_end) { const __half* dp = dz + (size_t)m * Cout + n; v = __half2float(dp[0]) + __half2float(dp[dz_ps]); }
+      ds[ml][n] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int ml = 0; ml < TM; ++ml) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(xs[pk[i]][ml], ds[ml][pn[i]], acc[i]);
+    }
+    __syncthreads();
+  }
+  float* op = part + (size_t)blockIdx.x * slab_stride;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + 256 * i;
+    if (idx < npairs) op[(size_t)pk[i] * cout_pad + pn[i]] = acc[i];
   }
 }
 __global__ void wgrad_reduce_scaled_kernel(const float* __restrict__ part, int slabs, size_t n, size_t slab_stride, const float* __restrict__ scale_dev,
@@ -708,7 +795,8 @@ extern "C" int yolo_train_init(yolo_handle* h, float* params_flat, float* grads_
     const size_t Mmax = (size_t)B * L.Ho * L.Wo;
     L.stat_groups = umma_stats_groups((int)Mmax);
     tmp[i].small = take((size_t)(4 + 2 + 2 + 4) * op.cout * 4);                // mean, rstd, rmean, rvar | mg[2] | ab[2] | dzscale (padded)
-    tmp[i].slab = take((size_t)kStatSlabs * 2 * op.cout * 8);
+    L.slab_cap = std::max(1, std::min(1024, kSlabCtas / ((op.cout + 255) / 256)));
+    tmp[i].slab = take((size_t)L.slab_cap * 2 * op.cout * 8);
     if (L.has_bn) {
       if (op.out.buf < 0) return hfail(h, fail(YOLO_E_UNSUPPORTED, "train_init: BatchNorm layer writing a user output"));
       L.z_ps = (long long)Mmax * op.cout;
@@ -938,9 +1026,9 @@ static int train_fwd_bwd(yolo_handle* h, const void* input, int in_layout, const
       bn_stats_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(L.z, L.z_ps, M, C, L.stat_part);
       ++g_launches;
     }
-    const int nslab = (int)std::max<size_t>(1, std::min<size_t>(kStatSlabs, groups / 64));
+    const int nslab = (int)std::max<size_t>(1, std::min<size_t>(std::min(L.slab_cap, kSlabCtas / ((C + 31) / 32)), groups / 32));
     reduce_groups_kernel<<<dim3((C + 31) / 32, nslab), 256, 0, st>>>(L.stat_part, groups, C, L.slab);
-    bn_finalize_fwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(L.slab, nslab, M, C, L.mean, L.rstd, L.rmean, L.rvar, T->bn_momentum, T->P + L.o_gamma,
+    bn_finalize_fwd_kernel<<<(C + 7) / 8, 256, 0, st>>>(L.slab, nslab, M, C, L.mean, L.rstd, L.rmean, L.rvar, T->bn_momentum, T->P + L.o_gamma,
                                                             T->P + L.o_beta, L.ab);
     const __half* res = op.has_res ? act16(h, op.res) : nullptr;
     {
@@ -991,13 +1079,15 @@ static int train_fwd_bwd(yolo_handle* h, const void* input, int in_layout, const
       const float* dy = grad_ptr(h, op.out);
       const int dyp = grad_pitch(op.out);
       float* dres = op.has_res ? grad_ptr(h, op.res) : nullptr;
-      YB_CUDA(cudaMemsetAsync(L.dzscale + 2, 0, 4, st));
+      YB_CUDA(cudaMemsetAsync(L.dzscale + 2, 0, 8, st));
       const int cb = std::min(C, 256);
-      const int nslab = std::max(1, std::min(kStatSlabs, M / 256));
+      const int red_lanes = 256 / (cb / 8);
+      const int nslab = std::max(1, std::min(std::min(L.slab_cap, kSlabCtas / ((C + cb - 1) / cb)), M / (red_lanes * 16)));
       bn_bwd_reduce_kernel<<<dim3((C + cb - 1) / cb, nslab), 256, 0, st>>>(L.z, L.z_ps, M, C, dy, dyp, op.out.coff, op.upsample2, L.Ho, L.Wo, L.mean,
                                                                          L.rstd, L.ab, op.act, dres, op.has_res ? grad_pitch(op.res) : 0, op.res.coff,
                                                                          L.slab, reinterpret_cast<unsigned int*>(L.dzscale + 2));
-      bn_bwd_finalize_kernel<<<1, 256, 0, st>>>(L.slab, nslab, M, C, T->P + L.o_gamma, L.rstd, L.mg, T->G + L.o_gamma, T->G + L.o_beta, L.dzscale);
+      bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(L.slab, nslab, M, C, L.ab, L.mg, T->G + L.o_gamma, T->G + L.o_beta,
+                                                          reinterpret_cast<unsigned int*>(L.dzscale + 3));
       {
         const int lanes = 256 / (cb / 8);
         const int rowblocks = std::max(1, std::min((M + kGuardRows + lanes - 1) / lanes, 148 * 8 / ((C + cb - 1) / cb)));
@@ -1011,10 +1101,16 @@ static int train_fwd_bwd(yolo_handle* h, const void* input, int in_layout, const
         rc = launch_wgrad_umma(L.wg, batch, T->G + L.o_w, op.cout_pad, 1.f, L.dzscale + 1, T->wg_scratch, T->wg_scratch_bytes, 0, st);
         if (rc) return hfail(h, rc);
       } else {
-        const int slabs = simt_wgrad_slabs(M, K, op.cout_pad);
+        int slabs = simt_wgrad_slabs(M, K, op.cout_pad);
         const size_t kn = (size_t)K * op.cout_pad;
         dim3 gw((K + 63) / 64, (op.cout_pad + 63) / 64, slabs);
         const void* xin = op.in.buf == -1 ? input : (const void*)act16(h, op.in);
+        if (op.in.buf == -1 && op.in.C == 3 && K <= 32 && C <= 32 && op.cout_pad == C && (size_t)K * C <= 1024) {
+          slabs = std::max(1, std::min(M / 256, kSlabCtas));
+          if ((size_t)slabs * kn * 4 > T->wg_scratch_bytes) slabs = std::max(1, (int)(T->wg_scratch_bytes / (kn * 4)));
+          stem_wgrad_kernel<<<slabs, 256, 0, st>>>(xin, lay, batch, op.in.H, op.in.W, L.dz, L.dz_plane_rows * C, L.Ho, L.Wo, C, op.kh, op.kw, op.stride,
+                                                   op.pad, T->wg_scratch, kn, op.cout_pad);
+        } else
         wgrad_simt_kernel<true, true><<<gw, 256, 0, st>>>(xin, op.in.ps, batch, op.in.H, op.in.W, op.in.C, op.in.cpitch, op.in.coff, lay, L.dz,
                                                          L.dz_plane_rows * C, C, L.Ho, L.Wo, C, op.kh, op.kw, op.stride, op.pad, T->wg_scratch, kn,
                                                          op.cout_pad);
@@ -1049,7 +1145,12 @@ static int train_fwd_bwd(yolo_handle* h, const void* input, int in_layout, const
     } else {
       // head conv (no BatchNorm, 90 / 10 channels): fp32 FFMA kernels on dz = d loss / d head
       float* dz = T->dheads[-2 - op.out.buf];
-      if (L.has_bias) colsum_kernel<<<(C + 31) / 32, 256, 0, st>>>(dz, M, C, T->G + L.o_bias);
+      if (L.has_bias) {
+        const int nslab = std::max(1, std::min(std::min(L.slab_cap, kSlabCtas / ((C + 31) / 32)), M / 64));
+        colsum_slab_kernel<<<dim3((C + 31) / 32, nslab), 256, 0, st>>>(dz, M, C, L.slab);
+        colsum_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(L.slab, nslab, C, T->G + L.o_bias);
+        ++g_launches;
+      }
       const int slabs = simt_wgrad_slabs(M, K, op.cout_pad);
       const size_t kn = (size_t)K * op.cout_pad;
       dim3 gw((K + 63) / 64, (op.cout_pad + 63) / 64, slabs);
