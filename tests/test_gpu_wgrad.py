@@ -38,6 +38,9 @@ CASES = [  # n, h, w, cin, cout, k, stride, pad
     (4, 13, 13, 256, 512, 3, 1, 1),
     (1, 13, 13, 512, 256, 1, 1, 0),
     (16, 52, 52, 128, 256, 3, 1, 1),      # a Darknet-53 layer at the training batch: splits + many pixel blocks
+    (2, 24, 24, 32, 64, 3, 2, 1),         # Cin = 32, plane-interleaved activations: the transposed kernel (stages.1.0)
+    (3, 20, 28, 32, 64, 3, 1, 1),         # ... stride 1 (stages.1.1.body.1)
+    (2, 16, 16, 32, 128, 1, 1, 0),        # ... two real dz blocks per tile, single tap
 ]
 
 

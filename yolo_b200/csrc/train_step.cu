@@ -924,7 +924,8 @@ extern "C" int yolo_train_init(yolo_handle* h, float* params_flat, float* grads_
         if (tmp[i].wT == (size_t)-1) return hfail(h, fail(YOLO_E_UNSUPPORTED, "train_init: no data-gradient kernel for layer %s", op.name.c_str()));
         L.wT = reinterpret_cast<float*>(T->arena + tmp[i].wT);
       }
-      if (wgrad_umma_eligible(cin, cout, op.kh, op.kw, op.in.dtype, op.in.il)) {
+      if (wgrad_umma_eligible(cin, cout, op.kh, op.kw, op.in.dtype, op.in.il) ||
+          wgrad_umma_il32_eligible(cin, cout, op.kh, op.kw, op.in.dtype, op.in.il, op.in.cpitch, op.in.coff)) {
         rc = wgrad_umma_plan(L.wg, act16(h, op.in), B, op.in.H, op.in.W, cin, op.in.cpitch, op.in.coff, op.kh, op.kw, op.stride, op.pad, L.dz,
                              L.dz_plane_rows, cout);
         if (rc) return hfail(h, rc);

@@ -216,6 +216,162 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   }
 }
 
+// ---- Cin = 32, plane-interleaved activations: the transposed problem -------------------------------------------------------------
+// A pixel row of such a tensor is [hi(32) | lo(32)] = 64 halves = one 128-byte row, so a 64-channel A unit does not exist.  Compute
+// dW^T instead:  D[n][j] = sum_m dz[m][n] * xrow[m][j],  n = output channel (A operand = dz, MN-major), j = 64 entries of the
+// interleaved row of one filter tap (B operand, MN-major).  One MMA against dz_hi yields dz_hi*x_hi (columns 0..31) AND dz_hi*x_lo
+// (columns 32..63); the one against dz_lo yields dz_lo*x_hi and the 2^-22 term dz_lo*x_lo; dW[tap*32 + c][n] = D[n][c] + D[n][32 + c]
+// is a sum inside one thread's registers.  Tile = 128 dz channels (Cout = 64: the 64-row block is read twice, LBO = 0, and the
+// duplicate rows are not stored) x 2 filter taps (N = 128); accumulation group g owns tap g of the pair.
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_il32_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int n_ablk = p.Cout >= 128 ? 2 : 1;                        // real 64-channel dz blocks per tile
+  const int a_bytes = 2 * n_ablk * WG_TILE_BYTES;                  // planes x blocks
+  const int stage_bytes = a_bytes + 2 * WG_TILE_BYTES;             // + two taps of interleaved activation rows
+  const uint32_t tiles_end = smem_base + p.stages * stage_bytes;
+  unsigned char* aux = smem_gen + (size_t)p.stages * stage_bytes;
+  const uint32_t bar_full = tiles_end, bar_empty = tiles_end + 8 * WG_MAX_STAGES;
+  const uint32_t bar_pfull = tiles_end + 16 * WG_MAX_STAGES, bar_pempty = bar_pfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 16 * WG_MAX_STAGES + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x;
+  const int split = unit % p.splits, tile = unit / p.splits;
+  const int tp = tile / p.n_tiles_n, mt = tile - tp * p.n_tiles_n;  // tap pair, 128-channel tile of dz
+  const int ntaps = p.n_units;                                      // kh*kw
+  const int nblk = (p.M + WG_PIX - 1) / WG_PIX;
+  const int pb_begin = (int)((long long)nblk * split / p.splits), pb_end = (int)((long long)nblk * (split + 1) / p.splits);
+  const int nstage_total = pb_end - pb_begin;
+  const int npart = (nstage_total + p.flush - 1) / p.flush;
+  constexpr int tmem_cols = 256;                                    // two 128-column partial buffers
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_x);
+    prefetch_tmap(&map_dz);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_pfull + 8 * b, 1); mbar_init(bar_pempty + 8 * b, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int HoWo = p.Ho * p.Wo;
+      int tap_r[2], tap_s[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        int tap = 2 * tp + u;
+        if (tap >= ntaps) tap = ntaps - 1;                          // odd tap count: the second half of the last tile is not stored
+        tap_r[u] = tap / p.kw; tap_s[u] = tap - tap_r[u] * p.kw;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pb = pb_begin; pb < pb_end; ++pb) {
+        const int m0 = pb * WG_PIX;
+        const int img = m0 / HoWo, rem = m0 - img * HoWo;
+        const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+        const int bw = ow * p.stride - p.pad, bh = oh * p.stride - p.pad;
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        const uint32_t full = bar_full + 8 * stage;
+        const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
+        mbar_expect_tx(full, (uint32_t)stage_bytes);
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl)
+          for (int j = 0; j < n_ablk; ++j)
+            tma_load_2d(sa + (pl * n_ablk + j) * WG_TILE_BYTES, &map_dz, full, mt * 128 + j * 64, (int)(m0 + pl * p.dz_plane_rows));
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          tma_load_im2col_4d(sb + u * WG_TILE_BYTES, &map_x, full, 0, bw, bh, img, (uint16_t)tap_s[u], (uint16_t)tap_r[u]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, true, 128, true, true);
+      const uint32_t a_lbo = n_ablk == 2 ? (uint32_t)WG_TILE_BYTES : 0u;      // one block: both 64-row halves read the same tile
+      int stage = 0;
+      uint32_t phase = 0, pcount = 0;
+      for (int i = 0; i < nstage_total; ++i) {
+        const int pbuf = pcount & 1;
+        const uint32_t tmem_main = tmem_base + pbuf * 128;
+        if (i % p.flush == 0) {
+          mbar_wait(bar_pempty + 8 * pbuf, ((pcount >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
+        uint32_t written = (i % p.flush == 0) ? 0u : 1u;
+        const uint64_t bdesc = make_smem_desc_mn(sb, (uint32_t)WG_TILE_BYTES, 1024u);
+#pragma unroll
+        for (int pi = 0; pi < 2; ++pi) {                                      // dz_lo first (small products), dz_hi closes the stage
+          const uint64_t adesc = make_smem_desc_mn(sa + (1 - pi) * n_ablk * WG_TILE_BYTES, a_lbo, 1024u);
+#pragma unroll
+          for (int k = 0; k < WG_PIX / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 128) >> 4);
+            umma_bf16(tmem_main, adesc + koff, bdesc + koff, idesc, written);
+            written = 1;
+          }
+        }
+        umma_commit(bar_empty + 8 * stage);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if ((i + 1) % p.flush == 0 || i + 1 == nstage_total) { umma_commit(bar_pfull + 8 * pbuf); ++pcount; }
+      }
+    }
+  } else {
+    const int group = (warp - 2) >> 2;                           // = tap of the pair
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;                        // dz channel within the tile
+    const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
+    float acc[2][32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[c][i] = 0.f;
+    for (int part = 0; part < npart; ++part) {
+      const int pbuf = part & 1;
+      mbar_wait(bar_pfull + 8 * pbuf, (part >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_addr + pbuf * 128 + group * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[c][i] += __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pempty + 8 * pbuf);
+    }
+    const int tap = 2 * tp + group;
+    const int n = mt * 128 + row;
+    if (tap < ntaps && row < n_ablk * 64 && n < p.Cout) {
+      const float sc = p.acc_scale * (p.acc_scale_dev ? __ldg(p.acc_scale_dev) : 1.f);
+      float* op = p.out + (size_t)split * p.out_split_stride + (size_t)(tap * 32) * p.cout_pad + n;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) op[(size_t)c * p.cout_pad] = (acc[0][c] + acc[1][c]) * sc;      // hi + lo halves of the interleaved row
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
 // G[i] = sum_s partial[s][i] in split order (deterministic)
 __global__ void wgrad_reduce_kernel(const float4* __restrict__ partial, int splits, size_t n4, size_t split_stride4, float4* __restrict__ out) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -228,26 +384,28 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ partial, int spli
   }
 }
 
+// planes `plane_stride` elements apart; plane_stride < dst_pitch = plane-interleaved rows ([hi(cols) | lo(cols)] per pixel)
 __global__ void split_f16x2_kernel(const float* __restrict__ src, long long rows, int cols, int src_pitch, float scale, const float* scale_dev,
                                    __half* __restrict__ dst, int dst_pitch, long long plane_stride, int* sat_flag) {
   const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.f);
-  const long long total = rows * dst_pitch;
+  const int iter_cols = plane_stride < dst_pitch ? cols : dst_pitch;       // planar: zero-fill the padding columns too
+  const long long total = rows * iter_cols;
   int sat = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / dst_pitch;
-    const int c = (int)(i - r * dst_pitch);
+    const long long r = i / iter_cols;
+    const int c = (int)(i - r * iter_cols);
     const float v = c < cols ? src[r * src_pitch + c] * sc : 0.f;
     if (fabsf(v) > kF16Max) sat = 1;
     const __half h = __float2half_rn(fminf(fmaxf(v, -kF16Max), kF16Max));
-    dst[i] = h;
-    dst[plane_stride + i] = __float2half_rn(v - __half2float(h));
+    dst[r * dst_pitch + c] = h;
+    dst[plane_stride + r * dst_pitch + c] = __float2half_rn(v - __half2float(h));
   }
   if (sat && sat_flag) atomicOr(sat_flag, YOLO_SAT_ACT_BN);
 }
 
 int launch_split_f16x2(const float* src, long long rows, int cols, int src_pitch, float scale, const float* scale_dev, void* dst, int dst_pitch,
                        long long plane_stride, int* sat_flag, cudaStream_t st) {
-  const long long total = rows * dst_pitch;
+  const long long total = rows * (plane_stride < dst_pitch ? cols : dst_pitch);
   if (total <= 0) return YOLO_OK;
   int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   split_f16x2_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, src_pitch, scale, scale_dev, static_cast<__half*>(dst), dst_pitch, plane_stride, sat_flag);
@@ -258,6 +416,10 @@ int launch_split_f16x2(const float* src, long long rows, int cols, int src_pitch
 
 bool wgrad_umma_eligible(int cin, int cout, int kh, int kw, int in_dtype, bool in_interleaved) {
   return cin % 64 == 0 && cout % 64 == 0 && kh == kw && in_dtype == DT_F16X2 && !in_interleaved;
+}
+
+bool wgrad_umma_il32_eligible(int cin, int cout, int kh, int kw, int in_dtype, bool in_interleaved, int cpitch, int coff) {
+  return cin == 32 && in_interleaved && cpitch == 64 && coff == 0 && (cout == 64 || cout % 128 == 0) && kh == kw && in_dtype == DT_F16X2;
 }
 
 int wgrad_umma_plan(WgradPlan& w, void* x_base, int x_plane_n, int H, int W, int cin, int cpitch, int coff, int kh, int kw, int stride, int pad,
@@ -273,8 +435,9 @@ int wgrad_umma_plan(WgradPlan& w, void* x_base, int x_plane_n, int H, int W, int
   w.Ho = (H + 2 * pad - kh) / stride + 1; w.Wo = (W + 2 * pad - kw) / stride + 1;
   w.in_coff = coff; w.x_plane_n = x_plane_n; w.dz_plane_rows = dz_plane_rows;
   w.bn = cout >= 256 && cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
+  w.il32 = cin == 32 && cpitch == 64;                       // plane-interleaved input: both planes in one 64-element row, N = images only
   {
-    cuuint64_t gdim[4] = {(cuuint64_t)cpitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)2 * x_plane_n};
+    cuuint64_t gdim[4] = {(cuuint64_t)cpitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(w.il32 ? 1 : 2) * x_plane_n};
     cuuint64_t gstr[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2};
     int lower[2] = {-pad, -pad};
     int upper[2] = {pad - (kw - 1), pad - (kh - 1)};
@@ -299,9 +462,9 @@ int wgrad_umma_plan(WgradPlan& w, void* x_base, int x_plane_n, int H, int W, int
 }
 
 static void wgrad_shape(const WgradPlan& w, int batch, int num_sms, int& k_tiles, int& n_tiles_n, int& splits) {
-  const int n_units = w.kh * w.kw * (w.cin / 64);
+  const int n_units = w.il32 ? w.kh * w.kw : w.kh * w.kw * (w.cin / 64);          // il32: units = filter taps, tiles pair them
   k_tiles = (n_units + 1) / 2;
-  n_tiles_n = w.cout / w.bn;
+  n_tiles_n = w.il32 ? (w.cout + 127) / 128 : w.cout / w.bn;
   const int tiles = k_tiles * n_tiles_n;
   const int nblk = (batch * w.Ho * w.Wo + WG_PIX - 1) / WG_PIX;
   // split the pixel range until the grid fills the SMs once, keeping at least 8 pixel blocks per split
@@ -330,7 +493,7 @@ int launch_wgrad_umma(const WgradPlan& w, int batch, float* dW, int cout_pad, fl
   int k_tiles;
   wgrad_shape(w, batch, num_sms, k_tiles, p.n_tiles_n, p.splits);
   p.M = batch * w.Ho * w.Wo;
-  p.n_units = w.kh * w.kw * (w.cin / 64); p.cin_blocks = w.cin / 64; p.kw = w.kw;
+  p.n_units = w.il32 ? w.kh * w.kw : w.kh * w.kw * (w.cin / 64); p.cin_blocks = w.il32 ? 1 : w.cin / 64; p.kw = w.kw;
   p.Ho = w.Ho; p.Wo = w.Wo; p.stride = w.stride; p.pad = w.pad;
   p.in_coff = w.in_coff; p.x_plane_n = w.x_plane_n; p.dz_plane_rows = w.dz_plane_rows;
   p.BN = w.bn;
@@ -344,7 +507,7 @@ int launch_wgrad_umma(const WgradPlan& w, int batch, float* dW, int cout_pad, fl
   } else {
     p.out = dW; p.out_split_stride = 0;
   }
-  const int stage_bytes = (4 + 2 * (p.BN / 64)) * WG_TILE_BYTES;
+  const int stage_bytes = w.il32 ? (2 * (w.cout >= 128 ? 2 : 1) + 2) * WG_TILE_BYTES : (4 + 2 * (p.BN / 64)) * WG_TILE_BYTES;
   const int aux_bytes = 16 * WG_MAX_STAGES + 64 + 64;
   int stages = (WG_SMEM_LIMIT - 1024 - aux_bytes) / stage_bytes;
   if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
@@ -352,10 +515,16 @@ int launch_wgrad_umma(const WgradPlan& w, int batch, float* dW, int cout_pad, fl
   p.stages = stages;
   p.flush = 2;                                                    // 8 full-magnitude MMA additions per TMEM partial, like the forward kernel
   const int smem_bytes = 1024 + stages * stage_bytes + aux_bytes;
-  rc = ensure_dyn_smem(reinterpret_cast<const void*>(&wgrad_umma_kernel), WG_SMEM_LIMIT);
-  if (rc) return rc;
   const int grid = k_tiles * p.n_tiles_n * p.splits;
-  wgrad_umma_kernel<<<grid, WG_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(w.map_x), *reinterpret_cast<const CUtensorMap*>(w.map_dz), p);
+  if (w.il32) {
+    rc = ensure_dyn_smem(reinterpret_cast<const void*>(&wgrad_il32_umma_kernel), WG_SMEM_LIMIT);
+    if (rc) return rc;
+    wgrad_il32_umma_kernel<<<grid, WG_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(w.map_x), *reinterpret_cast<const CUtensorMap*>(w.map_dz), p);
+  } else {
+    rc = ensure_dyn_smem(reinterpret_cast<const void*>(&wgrad_umma_kernel), WG_SMEM_LIMIT);
+    if (rc) return rc;
+    wgrad_umma_kernel<<<grid, WG_THREADS, smem_bytes, st>>>(*reinterpret_cast<const CUtensorMap*>(w.map_x), *reinterpret_cast<const CUtensorMap*>(w.map_dz), p);
+  }
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   if (p.splits > 1) {
@@ -376,7 +545,9 @@ extern "C" int yolo_debug_wgrad(const float* x, const float* dz, int n, int h, i
                                 int variant, void* stream) {
   using namespace yb;
   if (!x || !dz || !dW) return fail(YOLO_E_BADARG, "debug_wgrad: null argument");
-  if (!wgrad_umma_eligible(cin, cout, k, k, DT_F16X2, false)) return fail(YOLO_E_UNSUPPORTED, "debug_wgrad: needs cin %% 64 == 0 and cout %% 64 == 0");
+  const bool il = cin == 32;                                    // plane-interleaved activations -> the transposed kernel
+  if (!(il ? wgrad_umma_il32_eligible(cin, cout, k, k, DT_F16X2, true, 64, 0) : wgrad_umma_eligible(cin, cout, k, k, DT_F16X2, false)))
+    return fail(YOLO_E_UNSUPPORTED, "debug_wgrad: needs cin %% 64 == 0 and cout %% 64 == 0, or cin == 32 with cout == 64 / a multiple of 128");
   cudaStream_t st = (cudaStream_t)stream;
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
   const long long M = (long long)n * ho * wo;
@@ -387,10 +558,11 @@ extern "C" int yolo_debug_wgrad(const float* x, const float* dz, int n, int h, i
   YB_CUDA(cudaMalloc(reinterpret_cast<void**>(&xp), (size_t)2 * xrows * cin * 2));
   YB_CUDA(cudaMalloc(reinterpret_cast<void**>(&dzp), (size_t)2 * dz_plane_rows * cout * 2));
   YB_CUDA(cudaMemsetAsync(dzp, 0, (size_t)2 * dz_plane_rows * cout * 2, st));
-  int rc = launch_split_f16x2(x, xrows, cin, cin, 1.f, nullptr, xp, cin, xrows * cin, nullptr, st);
+  int rc = il ? launch_split_f16x2(x, xrows, 32, 32, 1.f, nullptr, xp, 64, 32, nullptr, st)
+              : launch_split_f16x2(x, xrows, cin, cin, 1.f, nullptr, xp, cin, xrows * cin, nullptr, st);
   if (!rc) rc = launch_split_f16x2(dz, M, cout, cout, 1.f, nullptr, dzp, cout, dz_plane_rows * cout, nullptr, st);
   WgradPlan plan;
-  if (!rc) rc = wgrad_umma_plan(plan, xp, n, h, w, cin, cin, 0, k, k, stride, pad, dzp, dz_plane_rows, cout);
+  if (!rc) rc = wgrad_umma_plan(plan, xp, n, h, w, cin, il ? 64 : cin, 0, k, k, stride, pad, dzp, dz_plane_rows, cout);
   if (!rc && !plan.enabled) rc = fail(YOLO_E_UNSUPPORTED, "debug_wgrad: plan not eligible");
   int sms = 0;
   if (!rc) rc = device_sm_count(&sms);

@@ -12,11 +12,14 @@ struct WgradPlan {
   int x_plane_n = 0;              // images per plane of the activation buffer (forward workspace: max_batch)
   long long dz_plane_rows = 0;    // pixel rows per plane of the dz matrix
   int bn = 0;                     // N tile (<= 256, multiple of 64)
+  bool il32 = false;              // Cin = 32 with plane-interleaved activations ([hi(32) | lo(32)] per pixel): the transposed kernel
   alignas(64) unsigned char map_x[128];    // im2col map over the layer input, box = 64 pixels x 64 channels
   alignas(64) unsigned char map_dz[128];   // tiled map over dz [planes * dz_plane_rows][Cout], box = 64 pixels x 64 channels
 };
 
 bool wgrad_umma_eligible(int cin, int cout, int kh, int kw, int in_dtype, bool in_interleaved);
+// Cin = 32, plane-interleaved input (cpitch 64): dW^T = dz^T x through the transposed kernel (Cout = 64 or a multiple of 128)
+bool wgrad_umma_il32_eligible(int cin, int cout, int kh, int kw, int in_dtype, bool in_interleaved, int cpitch, int coff);
 // x_base: first plane of the layer input buffer (NHWC, cpitch channels per pixel, planes x_plane_n images apart);
 // dz_base: [2][dz_plane_rows][cout] fp16 planes of the (scaled) pre-activation gradient, rows >= M zero up to the next multiple of 64.
 int wgrad_umma_plan(WgradPlan& w, void* x_base, int x_plane_n, int H, int W, int cin, int cpitch, int coff, int kh, int kw, int stride, int pad,
