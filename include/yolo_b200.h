@@ -31,6 +31,9 @@
  *   yolo_nccl_unique_id / yolo_train_comm_init
  *                                   <- kvstore 'device' gradient reduction inside trainer.step  car/YOLO.py:396
  *   yolo_get_param                  <- net.collect_params().save(...)  car/YOLO.py:546-549 (read-back for checkpoints)
+ *   yolo_azimuth                    <- softmax + atan2 of the orientation classes   car/video_node.py:244-252, yolo_cv.py:85-94
+ *   yolo_lp_corners / yolo_lp_unwarp <- ProjectRectangle6D.__call__ / add_edges    yolo_modules/licence_plate_render/__init__.py:340-402
+ *   yolo_lp_loss_targets            <- _find_best_LP + _loss_mask_LP + _get_loss_LP licence_plate/LP_detection.py:259-313,354-360
  *   yolo_predict_host               <- cv_img_2_ndarray + net.forward + predict + asnumpy
  *                                      yolo_modules/yolo_gluon.py:335-357, car/YOLO.py:597
  */
@@ -62,6 +65,7 @@ extern "C" {
 #define YOLO_NET_CARNET      0   /* BasicYOLONet topology + CarNet forward */
 #define YOLO_NET_CARLPNET    1   /* CarNet + licence-plate pose branch */
 #define YOLO_NET_LPDENSENET  2   /* DenseNet licence-plate detector */
+#define YOLO_NET_CARDENSENET 4   /* CarDenseNet (car/utils.py:48-61): the DenseNet with one YOLO head, NHWC output (B, H*W, A, C) */
 #define YOLO_NET_DEBUGCONV   3   /* kernel unit-test harness: conv "pre" (3 -> channels[0], 3x3) then conv "test"
                                     (channels[0] -> channels[1], k=layers[0], stride=layers[1], pad=layers[2],
                                     act=layers[3], residual=layers[4], bn=layers[5]); output fp32 NHWC */
@@ -191,6 +195,21 @@ size_t yolo_loss_scratch_bytes(int batch, int n_obj);
 int  yolo_loss_targets(const yolo_decode_geom* g, const void* const* heads, const float* labels, int batch, int n_obj,
                        const yolo_loss_params* p, void* scratch, float* out_losses, void* const* dheads, int32_t* out_assign,
                        void* stream);
+
+/* Post-decode consumers (device in, device out).
+ *   azimuth    : rows (B,row_len) as written by yolo_decode_top1; the last n_class entries are the orientation-class logits.
+ *                out_angle[b] = atan2(sum sin_k p_k, sum cos_k p_k), p = softmax, k*360/n_class degrees (car/video_node.py:244-252);
+ *                out_radius (may be NULL) = rows[b][0] * |mean vector| (yolo_cv.py:85-94).
+ *   lp_corners : poses rows hold [.., X, Y, Z (mm), r1, r2, r3 (rad), ..] starting at pose_offset (1 for yolo_decode_lp rows);
+ *                intrinsics = {fx, fy, cx, cy}; out_corners (B,4,2) = plate corners in pixels * (x_scale, y_scale)
+ *                (ProjectRectangle6D, yolo_modules/licence_plate_render/__init__.py:340-377).
+ *   lp_unwarp  : `add_edges` :379-402 - perspective crop of the frame (uint8 HWC, one frame for all plates or one per plate) to an
+ *                out_h x out_w x 3 plate image per set of corners; ok[b] = 0 where the quadrilateral is degenerate (crop zero-filled). */
+int  yolo_azimuth(const float* rows, int batch, int row_len, int n_class, float* out_angle, float* out_radius, void* stream);
+int  yolo_lp_corners(const float* poses, int batch, int pose_stride, int pose_offset, const double intrinsics[4], float x_scale,
+                     float y_scale, float* out_corners, void* stream);
+int  yolo_lp_unwarp(const unsigned char* img, int batch, int img_is_batched, int h, int w, const float* corners, int out_h, int out_w,
+                    unsigned char* out, int32_t* ok, void* stream);
 
 /* Licence-plate pose head: targets + the five LP losses (+ gradient of their sum w.r.t. the map) - `_find_best_LP`, `_loss_mask_LP`,
  * `_get_loss_LP` (licence_plate/LP_detection.py:259-313,354-360; `_score_weight_LP` car_and_LP/YOLO.py:124-131).

@@ -85,6 +85,15 @@ def spec_mid(size=(64, 64), C=10):
                 use_fp16=False)
 
 
+def _loss_check(losses, ref32, ref64, floor=2e-4):
+    """Per-image losses within max(floor, 2 x the fp32 oracle's own relative error) of the fp64 oracle."""
+    got, l32, l64 = losses.cpu().numpy().astype(np.float64), ref32["losses"].astype(np.float64), ref64["losses"]
+    den = np.maximum(np.abs(l64), 1e-8)
+    tol = np.maximum(floor, 2 * np.abs(l32 - l64) / den)
+    rel = np.abs(got - l64) / den
+    assert (rel <= tol).all(), f"loss rel err {rel.max():.2e} (tolerance {tol.flat[rel.argmax()]:.2e})\n{got}\n{l64}"
+
+
 def _grad_check(tr, shapes, ref32, ref64, floor=1e-3, names=None):
     """Relative L2 error of every gradient against the fp64 oracle <= max(floor, 2 x the fp32 oracle's own error)."""
     rows = []
@@ -117,7 +126,7 @@ def test_train_step_matches_oracle(spec, B):
     tr = yolo_b200.Trainer(net, learning_rate=0.001)
     xs = torch.from_numpy(x).cuda()
     losses = tr.forward_backward(xs, labels, hp["scale"], hp["positive_weight"], hp["negative_weight"])
-    np.testing.assert_allclose(losses.cpu().numpy(), ref["losses"], rtol=2e-4, atol=1e-8)
+    _loss_check(losses, ref, ref64)
     shapes = dict(net.param_shapes())
     worst = _grad_check(tr, shapes, ref, ref64)
     print(f"worst gradient rel L2 error {worst[0]:.2e} ({worst[1]})")
@@ -127,17 +136,20 @@ def test_train_step_matches_oracle(spec, B):
     assert torch.equal(g1, tr.G)
     assert net.saturated() == 0
     tr.step(B)
-    # Adam's first step moves every weight by ~lr*sign(g): where |g| is comparable to epsilon (1e-8) a 1e-10 difference in
-    # the gradient changes the update, so a handful of near-zero-gradient elements may differ by up to 2*lr.
-    n_bad = n_all = 0
+    # Adam's first step moves every weight by lr * g / (|g| + eps): where |g| / batch is comparable to epsilon (1e-8) a 1e-10 difference
+    # in the gradient changes the update (the fp32 oracle is just as uncertain there): those elements may differ by up to 2*lr; every
+    # element with a well-conditioned update (|g| / batch > 1e-6) must agree to 2 % of a step.
+    n_well = 0
     for name, v in ref["params"].items():
         if name.endswith(("running_mean", "running_var")):
             continue                                    # two forwards ran: checked separately below
         got = tr.get_param(name, shapes[name])
         diff = np.abs(got - v)
         assert diff.max() <= 2.1e-3 + 2e-5, f"{name}: {diff.max():.2e}"
-        n_bad += int((diff > 2e-5).sum()); n_all += diff.size
-    assert n_bad <= 2e-3 * n_all, f"{n_bad} of {n_all} parameters differ after the Adam step"
+        well = np.abs(ref64["grads"][name]) / B > 1e-6
+        assert diff[well].max(initial=0.0) <= 2e-5, f"{name}: {diff[well].max():.2e} on a well-conditioned element"
+        n_well += int(well.sum())
+    assert n_well > 100
     # the inference path now runs on the trained weights / refolded BN: compare it with the oracle evaluated on the
     # parameters READ BACK from the GPU (the oracle's own updated parameters differ in the few Adam sign-flip elements)
     back = {name: torch.from_numpy(tr.get_param(name, shp)) for name, shp in net.param_shapes()}
@@ -207,7 +219,7 @@ def test_train_step_dk53_416():
     net.load_params(params)
     tr = yolo_b200.Trainer(net)
     losses = tr.forward_backward(torch.from_numpy(x).cuda(), labels, hp["scale"], hp["positive_weight"], hp["negative_weight"])
-    np.testing.assert_allclose(losses.cpu().numpy(), ref["losses"], rtol=1e-3, atol=1e-8)
+    _loss_check(losses, ref, ref64, floor=1e-3)
     shapes = dict(net.param_shapes())
     names = ("yolo_outputs.0.weight", "yolo_outputs.2.bias", "yolo_blocks.2.tip.weight", "yolo_blocks.0.body.1.gamma", "stages.5.4.body.1.weight",
              "stages.4.0.weight", "stages.3.1.body.0.weight", "stages.2.0.weight", "stages.1.1.body.0.weight", "stages.1.0.weight", "stages.0.weight",
@@ -265,7 +277,7 @@ def test_car_and_lp_train_step():
     losses = y.trainer.forward_backward(xs, labels, y.scale, y.positive_weight, y.negative_weight, lp_labels=lp_labels,
                                         lp_positive_weight=y.LP_positive_weight, lp_negative_weight=y.LP_negative_weight)
     assert losses.shape == (10, B)
-    np.testing.assert_allclose(losses.cpu().numpy(), ref["losses"], rtol=2e-4, atol=1e-8)
+    _loss_check(losses, ref, ref64)
     worst = _grad_check(y.trainer, dict(y.net.param_shapes()), ref, ref64)
     print(f"car_and_LP worst gradient rel L2 error {worst[0]:.2e} ({worst[1]})")
     assert np.abs(y.trainer.get_param("LP_branch.5.weight", dict(y.net.param_shapes())["LP_branch.5.weight"], grad=True)).max() > 0

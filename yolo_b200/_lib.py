@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libyolo_b200.so")
 
 MAX_STAGES, MAX_SCALES, MAX_ANCHORS, MAX_BLOCKS = 8, 3, 8, 8
-NET_CARNET, NET_CARLPNET, NET_LPDENSENET, NET_DEBUGCONV = 0, 1, 2, 3
+NET_CARNET, NET_CARLPNET, NET_LPDENSENET, NET_DEBUGCONV, NET_CARDENSENET = 0, 1, 2, 3, 4
 PREC_FP32, PREC_BF16, PREC_BF16X6, PREC_FP16X3 = 0, 1, 2, 3
 IN_NCHW_F32, IN_NHWC_U8 = 0, 1
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x6": PREC_BF16X6, "fp16x3": PREC_FP16X3}
@@ -79,6 +79,9 @@ SYMBOLS = {
     "yolo_decode_lp": (_I, [_VP, _I, _I, _I, _I, _I, C.POINTER(C.c_float * 3), _VP, _VP, _VP]),
     "yolo_loss_scratch_bytes": (_SZ, [_I, _I]),
     "yolo_loss_targets": (_I, [C.POINTER(DecodeGeom), C.POINTER(_VP), _VP, _I, _I, C.POINTER(LossParams), _VP, _VP, C.POINTER(_VP), _VP, _VP]),
+    "yolo_azimuth": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP]),
+    "yolo_lp_corners": (_I, [_VP, _I, _I, _I, C.POINTER(C.c_double * 4), C.c_float, C.c_float, _VP, _VP]),
+    "yolo_lp_unwarp": (_I, [_VP, _I, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP]),
     "yolo_lp_loss_targets": (_I, [_VP, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_float * 3), _VP, _I, _I, C.POINTER(LpLossParams), _VP, _VP, _VP]),
     "yolo_train_forward_backward_lp": (_I, [_VP, _VP, _I, _VP, _I, _I, C.POINTER(LossParams), _VP, _I, _I, C.POINTER(LpLossParams), _VP, _VP]),
     "yolo_train_flat_size": (_SZ, [_VP]),

@@ -14,9 +14,10 @@ import torch
 
 from . import _lib
 from ._lib import (DecodeGeom, LossParams, LpLossParams, NmsParams, YoloSpec, check, IN_NCHW_F32, IN_NHWC_U8, NET_CARNET, NET_CARLPNET,
-                   NET_LPDENSENET, NET_DEBUGCONV, PRECISIONS)
+                   NET_LPDENSENET, NET_DEBUGCONV, NET_CARDENSENET, PRECISIONS)
 
-NET_TYPES = {"carnet": NET_CARNET, "carlpnet": NET_CARLPNET, "lpdensenet": NET_LPDENSENET, "debugconv": NET_DEBUGCONV}
+NET_TYPES = {"carnet": NET_CARNET, "carlpnet": NET_CARLPNET, "lpdensenet": NET_LPDENSENET, "debugconv": NET_DEBUGCONV,
+             "cardensenet": NET_CARDENSENET}
 
 
 def _require_cuda():
@@ -57,7 +58,9 @@ def _as_tensor(x):
 
 
 def init_steps(spec):
-    """car/YOLO.py:112-116."""
+    """car/YOLO.py:112-116 (DenseNet variants: the single head sits at stride 2^(len(block_config) + 1))."""
+    if "layers" not in spec:
+        return [2 ** (len(spec["block_config"]) + 1)]
     nd, npyr = len(spec["layers"]), len(spec["all_anchors"])
     start = nd - npyr + 1
     return [2 ** (start + i) for i in range(npyr)]
@@ -89,6 +92,12 @@ def make_c_spec(net_type, spec, precision="fp32", max_batch=1):
             for j, (ah, aw) in enumerate(sc):
                 s.anchors[i][j][0], s.anchors[i][j][1] = float(ah), float(aw)
         s.channels_per_anchor = int(sp[-1])
+    if net_type == "cardensenet":          # car/YOLO.py:864-893: one scale, A anchors, C channels per anchor
+        anchors = spec["all_anchors"]
+        s.n_scales, s.n_anchors = 1, len(anchors[0])
+        for j, (ah, aw) in enumerate(anchors[0]):
+            s.anchors[0][j][0], s.anchors[0][j][1] = float(ah), float(aw)
+        s.channels_per_anchor = int(spec["slice_point"][-1])
     if net_type in ("carlpnet", "lpdensenet"):
         s.lp_channels = int(spec["LP_slice_point"][-1])
         for i in range(3):
@@ -98,7 +107,7 @@ def make_c_spec(net_type, spec, precision="fp32", max_batch=1):
         s.channels[0], s.channels[1] = int(spec["cin"]), int(spec["cout"])
         for i, key in enumerate(("k", "stride", "pad", "act", "residual", "bn")):
             s.layers[i] = int(spec[key])
-    if net_type == "lpdensenet":
+    if net_type in ("lpdensenet", "cardensenet"):
         s.num_init_features, s.growth_rate = int(spec["num_init_features"]), int(spec["growth_rate"])
         cfg = spec["block_config"]
         s.n_blocks = len(cfg)
@@ -319,6 +328,57 @@ def decode_lp(lp, mode, r_max):
         check(lib.yolo_decode_lp(C.c_void_p(t.data_ptr()), B, hs, ws, ch, mode, C.byref(rm), C.c_void_p(rows.data_ptr()),
                                  C.c_void_p(idx.data_ptr()), _stream_ptr(t.device)))
     return rows, idx
+
+
+def azimuth(rows, n_class=24):
+    """car/video_node.py:244-252 / yolo_cv.cls2ang: rows (B,C) cuda fp32 from decode_top1 -> (angle (B,), radius (B,)) cuda fp32."""
+    lib = _lib.load()
+    t = _as_tensor(rows)
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 2):
+        raise ValueError("rows must be a contiguous (B, C) float32 CUDA tensor")
+    ang = torch.empty((t.shape[0],), dtype=torch.float32, device=t.device)
+    rad = torch.empty_like(ang)
+    with torch.cuda.device(t.device):
+        check(lib.yolo_azimuth(C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1], int(n_class), C.c_void_p(ang.data_ptr()), C.c_void_p(rad.data_ptr()),
+                               _stream_ptr(t.device)))
+    return ang, rad
+
+
+def lp_corners(poses, intrinsics, x_scale=1.0, y_scale=1.0, pose_offset=1):
+    """ProjectRectangle6D.__call__ (licence_plate_render/__init__.py:340-377): poses (B,>=offset+6) cuda fp32 rows holding
+    [X, Y, Z (mm), r1, r2, r3 (rad)] at ``pose_offset`` (1 for predict_LP rows); intrinsics = (fx, fy, cx, cy) -> (B,4,2) pixel corners."""
+    lib = _lib.load()
+    t = _as_tensor(poses)
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 2):
+        raise ValueError("poses must be a contiguous (B, n) float32 CUDA tensor")
+    out = torch.empty((t.shape[0], 4, 2), dtype=torch.float32, device=t.device)
+    k = (C.c_double * 4)(*[float(v) for v in intrinsics])
+    with torch.cuda.device(t.device):
+        check(lib.yolo_lp_corners(C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1], int(pose_offset), C.byref(k), float(x_scale), float(y_scale),
+                                  C.c_void_p(out.data_ptr()), _stream_ptr(t.device)))
+    return out
+
+
+def lp_unwarp(img, corners, LP_size=(160, 380)):
+    """``add_edges`` (licence_plate_render/__init__.py:379-402): img (H,W,3) or (B,H,W,3) cuda uint8, corners (B,4,2) cuda fp32 ->
+    (clipped plates (B, LP_size[0], LP_size[1], 3) uint8, ok (B,) int32)."""
+    lib = _lib.load()
+    im, cn = _as_tensor(img), _as_tensor(corners)
+    if not (im.is_cuda and im.dtype == torch.uint8 and im.is_contiguous() and im.dim() in (3, 4) and im.shape[-1] == 3):
+        raise ValueError("img must be a contiguous uint8 CUDA tensor (H,W,3) or (B,H,W,3)")
+    if not (cn.is_cuda and cn.dtype == torch.float32 and cn.is_contiguous() and tuple(cn.shape[1:]) == (4, 2)):
+        raise ValueError("corners must be a contiguous (B,4,2) float32 CUDA tensor")
+    B = cn.shape[0]
+    batched = im.dim() == 4
+    if batched and im.shape[0] != B:
+        raise ValueError("one frame per plate, or a single frame")
+    H, W = im.shape[-3], im.shape[-2]
+    out = torch.empty((B, LP_size[0], LP_size[1], 3), dtype=torch.uint8, device=im.device)
+    ok = torch.empty((B,), dtype=torch.int32, device=im.device)
+    with torch.cuda.device(im.device):
+        check(lib.yolo_lp_unwarp(C.c_void_p(im.data_ptr()), B, int(batched), H, W, C.c_void_p(cn.data_ptr()), LP_size[0], LP_size[1],
+                                 C.c_void_p(out.data_ptr()), C.c_void_p(ok.data_ptr()), _stream_ptr(im.device)))
+    return out, ok
 
 
 def loss_targets(spec, heads, labels, scale, positive_weight, negative_weight, car_rotate=False, with_grad=False, steps=None):

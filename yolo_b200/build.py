@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libyolo_b200.so")
-SOURCES = ["net.cu", "decode.cu", "conv_simt.cu", "conv_umma.cu", "wgrad_umma.cu", "train_loss.cu", "train_step.cu"]
+SOURCES = ["net.cu", "decode.cu", "conv_simt.cu", "conv_umma.cu", "wgrad_umma.cu", "train_loss.cu", "train_step.cu", "post.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr", "-cudart", "static"]
 

@@ -276,7 +276,9 @@ struct Builder {
     return YOLO_OK;
   }
 
-  int build_lpdense() {
+  // dense_yolo: CarDenseNet (car/utils.py:48-61) = the same DenseNet with (7 + classes) = A*C output channels, returned NHWC as
+  // (B, H*W, A, C) like a YOLO head (x.transpose((0, 2, 3, 1)).reshape((0, -1, A, C)))
+  int build_lpdense(bool dense_yolo = false) {
     const yolo_spec& s = h->spec;
     if (s.n_blocks < 1 || s.n_blocks > YOLO_MAX_BLOCKS || s.num_init_features < 1 || s.growth_rate < 1 || s.bn_size < 1)
       return fail(YOLO_E_BADARG, "spec: DenseNet parameters invalid");
@@ -316,10 +318,11 @@ struct Builder {
     }
     View xin = slice(blk, 0, nf);
     View t = conv("", "tail.conv1", xin, 512, 3, 1, 1, ACT_RELU, "tail.bn2", "tail.conv1", "tail.bn1");
-    const int nout = 7 + s.lp_num_class;
+    const int nout = dense_yolo ? s.n_anchors * s.channels_per_anchor : 7 + s.lp_num_class;
+    if (dense_yolo && (s.n_anchors < 1 || s.n_anchors > YOLO_MAX_ANCHORS || s.channels_per_anchor < 6)) return fail(YOLO_E_BADARG, "spec: CarDenseNet anchors/channels invalid");
     View o;
     o.buf = -2; o.H = t.H; o.W = t.W; o.C = nout; o.cpitch = nout; o.coff = 0; o.dtype = DT_F32;
-    conv("tail.conv2", "tail.conv2", t, nout, 1, 0, 1, ACT_NONE, "", "tail.conv2", "", &o, nullptr, 0, /*out_nchw=*/1);
+    conv("tail.conv2", "tail.conv2", t, nout, 1, 0, 1, ACT_NONE, "", "tail.conv2", "", &o, nullptr, 0, /*out_nchw=*/dense_yolo ? 0 : 1);
     h->outputs.resize(1);
     h->outputs[0] = o;
     return YOLO_OK;
@@ -389,6 +392,7 @@ extern "C" int yolo_create(const yolo_spec* spec, int device, yolo_handle** out)
       rc = b.build_yolo(true);
       break;
     case YOLO_NET_LPDENSENET: rc = b.build_lpdense(); break;
+    case YOLO_NET_CARDENSENET: rc = b.build_lpdense(true); break;
     case YOLO_NET_DEBUGCONV: rc = b.build_debugconv(); break;
     default: return fail(YOLO_E_BADARG, "create: net_type=%d", spec->net_type);
   }
@@ -570,6 +574,8 @@ extern "C" int yolo_output_shape(const yolo_handle* h, int index, int32_t shape[
   const yolo_spec& s = h->spec;
   if (s.net_type == YOLO_NET_LPDENSENET) {
     shape[0] = v.C; shape[1] = v.H; shape[2] = v.W; shape[3] = 1; *ndim = 3;
+  } else if (s.net_type == YOLO_NET_CARDENSENET) {
+    shape[0] = v.H * v.W; shape[1] = s.n_anchors; shape[2] = s.channels_per_anchor; shape[3] = 1; *ndim = 3;
   } else if (s.net_type == YOLO_NET_DEBUGCONV) {
     shape[0] = v.H; shape[1] = v.W; shape[2] = v.C; shape[3] = 1; *ndim = 3;
   } else if (index < s.n_scales) {
@@ -663,7 +669,7 @@ extern "C" int yolo_predict_host(yolo_handle* h, const void* host_input, int bat
                                  int32_t* host_idx, void* stream) {
   if (!h || !host_input || !host_rows) return fail(YOLO_E_BADARG, "predict_host: null argument");
   const yolo_spec& s = h->spec;
-  if (s.net_type == YOLO_NET_LPDENSENET) return hfail(h, fail(YOLO_E_UNSUPPORTED, "predict_host: CARNET/CARLPNET only"));
+  if (s.net_type == YOLO_NET_LPDENSENET || s.net_type == YOLO_NET_CARDENSENET) return hfail(h, fail(YOLO_E_UNSUPPORTED, "predict_host: CARNET/CARLPNET only"));
   if (batch < 1 || batch > s.max_batch) return hfail(h, fail(YOLO_E_SHAPE, "predict_host: batch=%d outside [1,%d]", batch, s.max_batch));
   YB_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;

@@ -160,6 +160,53 @@ class YOLO:
     train_step = _train_batch          # north-star name of the same call
 
 
+class YOLO_dense(YOLO):
+    """car/YOLO.py:864-937: the DenseNet-backed detector (``CarDenseNet``, car/utils.py:48-61) - one head of A anchors at stride 32;
+    ``predict`` is the same decode with a single scale ((1, 160, 5, 30) at 320 x 512)."""
+
+    net_type = "cardensenet"
+
+    def predict(self, batch_out, **kw):
+        batch_out = batch_out if isinstance(batch_out, (list, tuple)) else [batch_out]          # car/YOLO.py:897
+        return YOLO.predict(self, batch_out, **kw)
+
+
+class ProjectRectangle6D:
+    """yolo_modules/licence_plate_render/__init__.py:274-402 on the GPU: plate corners under a 6-D pose and the perspective crop.
+    ``camera`` = dict(image_width, image_height, fx, fy, cx, cy) (the reference reads them from its camera yaml, :279-286)."""
+
+    def __init__(self, camera, device=0):
+        self.camera_w, self.camera_h = camera["image_width"], camera["image_height"]
+        self.fx, self.fy, self.cx, self.cy = camera["fx"], camera["fy"], camera["cx"], camera["cy"]
+        self.device = torch.device("cuda", device)
+
+    def _poses(self, pose_6d):
+        p = torch.as_tensor(np.asarray(pose_6d, np.float32) if not torch.is_tensor(pose_6d) else pose_6d, dtype=torch.float32)
+        return p.reshape(-1, p.shape[-1]).to(self.device).contiguous()
+
+    def __call__(self, pose_6d):
+        """[X, Y, Z (mm), r1, r2, r3 (rad)] -> (4, 2) float32 corner points (:340-353); a (B, 6) batch gives (B, 4, 2)."""
+        p = self._poses(pose_6d)
+        out = api.lp_corners(p, (self.fx, self.fy, self.cx, self.cy), pose_offset=0).cpu().numpy()
+        return out[0] if np.ndim(pose_6d) == 1 else out
+
+    def add_edges(self, img, pose, LP_size=(160, 380)):
+        """:379-402: returns (corner points scaled to ``img``, clipped plate).  ``img``: (H, W, 3) uint8 numpy / cuda tensor.  The polyline
+        overlay of the reference is drawing, left to the caller (cv2.polylines on the returned corners)."""
+        im = torch.as_tensor(img).to(self.device).contiguous()
+        p = self._poses(pose)
+        corners = api.lp_corners(p[:1], (self.fx, self.fy, self.cx, self.cy), im.shape[1] / float(self.camera_w), im.shape[0] / float(self.camera_h), 0)
+        clipped, ok = api.lp_unwarp(im, corners, LP_size)
+        return corners[0].cpu().numpy(), clipped[0].cpu().numpy()
+
+
+def cls2ang(rows, n_class=24):
+    """yolo_cv.cls2ang / car/video_node.py:244-252 for predict() rows: -> (vec_ang (B,), vec_rad (B,)) numpy."""
+    t = rows if torch.is_tensor(rows) else torch.from_numpy(np.ascontiguousarray(rows, np.float32)).cuda()
+    ang, rad = api.azimuth(t.contiguous(), n_class)
+    return ang.cpu().numpy(), rad.cpu().numpy()
+
+
 class CarLPYOLO(YOLO):
     """car_and_LP/YOLO.py ``YOLO``: CarLPNet + predict_LP."""
 
