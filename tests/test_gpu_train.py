@@ -141,7 +141,7 @@ def test_train_step_matches_oracle(spec, B):
     tr.step(B)
     # Adam's first step moves every weight by lr * g / (|g| + eps): where |g| / batch is comparable to epsilon (1e-8) a 1e-10 difference
     # in the gradient changes the update (the fp32 oracle is just as uncertain there): those elements may differ by up to 2*lr; every
-    # element with a well-conditioned update (|g| / batch > 1e-6) must agree to 2 % of a step.
+    # element with a well-conditioned update (|g| / batch > 1e-5 = 30 x Adam's effective epsilon eps / sqrt(1 - beta2)) must agree to 2 % of a step.
     n_well = 0
     for name, v in ref["params"].items():
         if name.endswith(("running_mean", "running_var")):
@@ -149,7 +149,7 @@ def test_train_step_matches_oracle(spec, B):
         got = tr.get_param(name, shapes[name])
         diff = np.abs(got - v)
         assert diff.max() <= 2.1e-3 + 2e-5, f"{name}: {diff.max():.2e}"
-        well = np.abs(ref64["grads"][name]) / B > 1e-6
+        well = np.abs(ref64["grads"][name]) / B > 1e-5
         assert diff[well].max(initial=0.0) <= 2e-5, f"{name}: {diff[well].max():.2e} on a well-conditioned element"
         n_well += int(well.sum())
     assert n_well > 100
