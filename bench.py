@@ -234,6 +234,7 @@ def parity_block(spec, params, frames_u8, heads, pred, idx, f64_images=(0, 31)):
     import numpy as np
     import torch
     from oracle import decode, nets
+    torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))      # torchrun pins OMP_NUM_THREADS=1; the checker may use the host cores
     x = (frames_u8.astype(np.float32).transpose(0, 3, 1, 2) / np.float32(255)).astype(np.float32)
 
     def run(dtype, images, chunk):

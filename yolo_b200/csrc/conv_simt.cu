@@ -401,7 +401,9 @@ int launch_conv_simt(const ConvDesc& d, int in_layout, cudaStream_t st) {
 // activation in the precision's storage format.  (K = 27 is too small for the tensor cores; this layer is
 // bound by its output write.)
 constexpr int STEM_CO = 16;
-template <class FO, int LAYOUT>
+// PX = output pixels per thread (consecutive in the flat pixel index).  With one pixel per thread the kernel is co-limited by the FMA
+// pipe and the shared-memory pipe (one broadcast LDS.128 of weights per 4 FMAs); two pixels per thread reuse every weight load twice.
+template <class FO, int LAYOUT, int PX>
 __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ ConvKArgs args) {
   using TOut = typename FO::T;
   const ConvDesc& d = args.d;
@@ -415,83 +417,93 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
     s_sh[i] = d.shift ? __ldg(d.shift + i) : 0.f;
   }
   __syncthreads();
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int HoWo = d.Ho * d.Wo;
-  const int mm = m < args.M ? m : args.M - 1;
-  const int n = mm / HoWo, rem = mm - n * HoWo;
-  const int oh = rem / d.Wo, ow = rem - oh * d.Wo;
-  float x[27];
+  const int m_blk0 = blockIdx.x * blockDim.x * PX;
+  float x[PX][27];
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+  for (int p = 0; p < PX; ++p) {
+    const int m = m_blk0 + threadIdx.x * PX + p;
+    const int mm = m < args.M ? m : args.M - 1;
+    const int n = mm / HoWo, rem = mm - n * HoWo;
+    const int oh = rem / d.Wo, ow = rem - oh * d.Wo;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int ih = oh * d.stride - d.pad + r, iw = ow * d.stride - d.pad + q;
-      const bool ok = (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W;
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = 0.f;
-        if (ok) {
-          if (LAYOUT == IN_NCHW_F32) v = __ldg(static_cast<const float*>(d.in) + ((size_t)(n * 3 + c) * d.H + ih) * d.W + iw);
-          else v = (float)__ldg(static_cast<const unsigned char*>(d.in) + ((size_t)(n * d.H + ih) * d.W + iw) * 3 + c) / 255.f;
+      for (int q = 0; q < 3; ++q) {
+        const int ih = oh * d.stride - d.pad + r, iw = ow * d.stride - d.pad + q;
+        const bool ok = (unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v = 0.f;
+          if (ok) {
+            if (LAYOUT == IN_NCHW_F32) v = __ldg(static_cast<const float*>(d.in) + ((size_t)(n * 3 + c) * d.H + ih) * d.W + iw);
+            else v = (float)__ldg(static_cast<const unsigned char*>(d.in) + ((size_t)(n * d.H + ih) * d.W + iw) * 3 + c) / 255.f;
+          }
+          x[p][(r * 3 + q) * 3 + c] = v;
         }
-        x[(r * 3 + q) * 3 + c] = v;
       }
-    }
-  // Results are staged in shared memory as whole pixel rows so that the block writes its 256 consecutive pixels with
+  }
+  // Results are staged in shared memory as whole pixel rows so that the block writes its 256*PX consecutive pixels with
   // fully coalesced 16-byte stores (a thread-per-pixel store pattern touches 32 different lines per instruction).
-  TOut* s_out = reinterpret_cast<TOut*>(s_sh + d.Cout);          // [NP][256][Cout]
+  TOut* s_out = reinterpret_cast<TOut*>(s_sh + d.Cout);          // [NP][256*PX][Cout]
+  const int blk_pix = (int)blockDim.x * PX;
   const bool staged = args.in_layout >= 0 && (d.Cout * sizeof(TOut)) % 16 == 0 && (d.out_cpitch * sizeof(TOut)) % 16 == 0 &&
                       (d.out_coff * sizeof(TOut)) % 16 == 0 && (d.out_plane_stride * sizeof(TOut)) % 16 == 0;
-  TOut* op = static_cast<TOut*>(d.out) + (size_t)m * d.out_cpitch + d.out_coff;
-  const int m_blk0 = blockIdx.x * blockDim.x;
   constexpr int SW_E = 16 / (int)sizeof(TOut);                     // elements per 16-byte vector
   const int sw_vpp = d.Cout / SW_E;                                // vectors per pixel row (power of two: Cout is 16 or 32)
   const int sw_rpl = max(1, 128 / (d.Cout * (int)sizeof(TOut)));   // pixel rows per 128-byte bank line
-  const int sw_x = ((int)threadIdx.x / sw_rpl) & (sw_vpp - 1);
   int sat = 0;
   for (int o0 = 0; o0 < d.Cout; o0 += STEM_CO) {
-    float acc[STEM_CO];
+    float acc[PX][STEM_CO];
 #pragma unroll
-    for (int j = 0; j < STEM_CO; ++j) acc[j] = 0.f;
-    if (m < args.M) {
+    for (int p = 0; p < PX; ++p)
 #pragma unroll
-      for (int k = 0; k < 27; ++k) {
+      for (int j = 0; j < STEM_CO; ++j) acc[p][j] = 0.f;
 #pragma unroll
-        for (int j4 = 0; j4 < STEM_CO; j4 += 4) {
-          const float4 w = *reinterpret_cast<const float4*>(&s_w[k * cp + o0 + j4]);
-          acc[j4] = fmaf(x[k], w.x, acc[j4]);
-          acc[j4 + 1] = fmaf(x[k], w.y, acc[j4 + 1]);
-          acc[j4 + 2] = fmaf(x[k], w.z, acc[j4 + 2]);
-          acc[j4 + 3] = fmaf(x[k], w.w, acc[j4 + 3]);
+    for (int k = 0; k < 27; ++k) {
+#pragma unroll
+      for (int j4 = 0; j4 < STEM_CO; j4 += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(&s_w[k * cp + o0 + j4]);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          acc[p][j4] = fmaf(x[p][k], w.x, acc[p][j4]);
+          acc[p][j4 + 1] = fmaf(x[p][k], w.y, acc[p][j4 + 1]);
+          acc[p][j4 + 2] = fmaf(x[p][k], w.z, acc[p][j4 + 2]);
+          acc[p][j4 + 3] = fmaf(x[p][k], w.w, acc[p][j4 + 3]);
         }
       }
     }
 #pragma unroll
-    for (int j4 = 0; j4 < STEM_CO; j4 += 4) {
-      float v[4];
+    for (int p = 0; p < PX; ++p) {
+      const int pl = threadIdx.x * PX + p, m = m_blk0 + pl;          // pixel within the block / flat pixel
+      const int sw_x = (pl / sw_rpl) & (sw_vpp - 1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float y = fmaf(acc[j4 + j], s_sc[o0 + j4 + j], s_sh[o0 + j4 + j]);
-        if (d.act == ACT_LEAKY) y = y > 0.f ? y : 0.1f * y;
-        else if (d.act == ACT_RELU) y = fmaxf(y, 0.f);
-        v[j] = y;
+      for (int j4 = 0; j4 < STEM_CO; j4 += 4) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float y = fmaf(acc[p][j4 + j], s_sc[o0 + j4 + j], s_sh[o0 + j4 + j]);
+          if (d.act == ACT_LEAKY) y = y > 0.f ? y : 0.1f * y;
+          else if (d.act == ACT_RELU) y = fmaxf(y, 0.f);
+          v[j] = m < args.M ? y : 0.f;
+        }
+        if (staged) {
+          // 16-byte vectors of a pixel row are XOR-swizzled with the pixel index: a plain [pixel][Cout] staging buffer puts the
+          // 32 threads of a store on 2-4 banks (row pitch 64/128 bytes), 16-way conflicts; un-swizzled again by the copy-out
+          const int e = o0 + j4, vi = e / SW_E, within = e - vi * SW_E;
+          store4f<FO>(s_out + (size_t)pl * d.Cout + ((vi ^ sw_x) * SW_E) + within, (long long)blk_pix * d.Cout, v, sat);
+        } else if (m < args.M) store4f<FO>(static_cast<TOut*>(d.out) + (size_t)m * d.out_cpitch + d.out_coff + o0 + j4, d.out_plane_stride, v, sat);
       }
-      if (staged) {
-        // 16-byte vectors of a pixel row are XOR-swizzled with the pixel index: a plain [pixel][Cout] staging buffer puts the
-        // 32 threads of a store on 2-4 banks (row pitch 64/128 bytes), 16-way conflicts; un-swizzled again by the copy-out
-        const int e = o0 + j4, vi = e / SW_E, within = e - vi * SW_E;
-        store4f<FO>(s_out + (size_t)threadIdx.x * d.Cout + ((vi ^ sw_x) * SW_E) + within, (long long)blockDim.x * d.Cout, v, sat);
-      } else if (m < args.M) store4f<FO>(op + o0 + j4, d.out_plane_stride, v, sat);
     }
   }
   if (sat && d.sat_flag) atomicOr(d.sat_flag, YOLO_SAT_ACT_FFMA);
   if (staged) {
     __syncthreads();
-    const int rows = min((int)blockDim.x, args.M - m_blk0);
+    const int rows = min(blk_pix, args.M - m_blk0);
     const int vec_per_plane = rows * d.Cout * (int)sizeof(TOut) / 16;
 #pragma unroll
     for (int q = 0; q < FO::NP; ++q) {
-      const uint4* src = reinterpret_cast<const uint4*>(s_out + (size_t)q * blockDim.x * d.Cout);
+      const uint4* src = reinterpret_cast<const uint4*>(s_out + (size_t)q * blk_pix * d.Cout);
       TOut* dst = static_cast<TOut*>(d.out) + (size_t)q * d.out_plane_stride + (size_t)m_blk0 * d.out_cpitch + d.out_coff;
       for (int i = threadIdx.x; i < vec_per_plane; i += blockDim.x) {
         const int pix = i / sw_vpp, vi = i - pix * sw_vpp;
@@ -501,14 +513,16 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
   }
 }
 
-template <class FO>
-static void launch_stem_t(const ConvKArgs& a, int in_layout, int smem, cudaStream_t st) {
-  const int blocks = (a.M + 255) / 256;
-  // three staged 16-bit planes need more than the default 48 KB
-  ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_kernel<FO, IN_NCHW_F32>), 96 * 1024);
-  ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_kernel<FO, IN_NHWC_U8>), 96 * 1024);
-  if (in_layout == IN_NCHW_F32) stem3x3_kernel<FO, IN_NCHW_F32><<<blocks, 256, smem, st>>>(a);
-  else stem3x3_kernel<FO, IN_NHWC_U8><<<blocks, 256, smem, st>>>(a);
+template <class FO, int PX>
+static int launch_stem_t(const ConvKArgs& a, int in_layout, int smem, cudaStream_t st) {
+  const int blocks = (a.M + 256 * PX - 1) / (256 * PX);
+  // staged 16-bit planes need more than the default 48 KB
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_kernel<FO, IN_NCHW_F32, PX>), 160 * 1024);
+  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_kernel<FO, IN_NHWC_U8, PX>), 160 * 1024);
+  if (rc) return rc;
+  if (in_layout == IN_NCHW_F32) stem3x3_kernel<FO, IN_NCHW_F32, PX><<<blocks, 256, smem, st>>>(a);
+  else stem3x3_kernel<FO, IN_NHWC_U8, PX><<<blocks, 256, smem, st>>>(a);
+  return YOLO_OK;
 }
 
 bool stem_eligible(const ConvDesc& d, int in_layout) {
@@ -524,13 +538,16 @@ int launch_stem(const ConvDesc& d, int in_layout, cudaStream_t st) {
   a.M = d.N * d.Ho * d.Wo;
   a.K = 27;
   const int esz = d.out_dtype == DT_F32 ? 4 : 2, npl = dtype_planes(d.out_dtype);
-  const int smem = (27 * d.cout_pad + 2 * d.Cout) * 4 + npl * 256 * d.Cout * esz;      // weights, scale/shift, staged output rows
+  auto smem_for = [&](int px) { return (27 * d.cout_pad + 2 * d.Cout) * 4 + npl * 256 * px * d.Cout * esz; };   // weights, scale/shift, staged rows
+  const bool two = smem_for(2) <= 150 * 1024;                 // two pixels per thread whenever the staged rows fit
+  int rc;
   switch (d.out_dtype) {
-    case DT_F32: launch_stem_t<FmtF32>(a, in_layout, smem, st); break;
-    case DT_BF16: launch_stem_t<FmtBF16>(a, in_layout, smem, st); break;
-    case DT_BF16X3: launch_stem_t<FmtBF16X3>(a, in_layout, smem, st); break;
-    default: launch_stem_t<FmtF16X2>(a, in_layout, smem, st); break;
+    case DT_F32: rc = two ? launch_stem_t<FmtF32, 2>(a, in_layout, smem_for(2), st) : launch_stem_t<FmtF32, 1>(a, in_layout, smem_for(1), st); break;
+    case DT_BF16: rc = two ? launch_stem_t<FmtBF16, 2>(a, in_layout, smem_for(2), st) : launch_stem_t<FmtBF16, 1>(a, in_layout, smem_for(1), st); break;
+    case DT_BF16X3: rc = two ? launch_stem_t<FmtBF16X3, 2>(a, in_layout, smem_for(2), st) : launch_stem_t<FmtBF16X3, 1>(a, in_layout, smem_for(1), st); break;
+    default: rc = two ? launch_stem_t<FmtF16X2, 2>(a, in_layout, smem_for(2), st) : launch_stem_t<FmtF16X2, 1>(a, in_layout, smem_for(1), st); break;
   }
+  if (rc) return rc;
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
