@@ -280,7 +280,9 @@ def test_car_and_lp_train_step():
     losses = y.trainer.forward_backward(xs, labels, y.scale, y.positive_weight, y.negative_weight, lp_labels=lp_labels,
                                         lp_positive_weight=y.LP_positive_weight, lp_negative_weight=y.LP_negative_weight)
     assert losses.shape == (10, B)
-    _loss_check(losses, ref, ref64)
+    # the LP losses sit behind 31 chained convolutions with batch-statistics BatchNorm on a 2-image batch: small differences d = pred - target
+    # carry the logit noise with a gain of 2/d (the fp32 oracle itself is 5e-4 off on them)
+    _loss_check(losses, ref, ref64, floor=np.array([[2e-4]] * 5 + [[2e-3]] * 5))
     worst = _grad_check(y.trainer, dict(y.net.param_shapes()), ref, ref64)
     print(f"car_and_LP worst gradient rel L2 error {worst[0]:.2e} ({worst[1]})")
     assert np.abs(y.trainer.get_param("LP_branch.5.weight", dict(y.net.param_shapes())["LP_branch.5.weight"], grad=True)).max() > 0
