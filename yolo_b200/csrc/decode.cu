@@ -90,11 +90,12 @@ struct NmsDev {
 };
 
 struct NmsSmem {
-  unsigned long long keys[kMaxRaw];
+  unsigned long long keys[kMaxRaw];      // raw candidates (rank 0 gathers them; every CTA takes a copy)
+  unsigned long long sorted[kMaxCand];   // the best K candidates in (score desc, index asc) order
   float4 box[kMaxCand];
   int cls[kMaxCand];
   int keep[kMaxCand];
-  unsigned alive[kMaxCand / 32];
+  unsigned mask[kMaxCand * (kMaxCand / 32)];   // rank 0: bit j of row i = "i suppresses j" (j > i, same class, IoU > thr)
 };
 
 template <int MODE>   // 0 = top-1 (reference semantics), 1 = NMS extension
@@ -160,20 +161,22 @@ decode_kernel(const __grid_constant__ DecodeDev g, const NmsDev np, float* __res
     }
   }
   cluster.sync();                       // partials (and candidates) have landed in rank 0
-  if (rank != 0) return;
+  if (MODE == 0 && rank != 0) return;
 
-  // ---- rank 0: final top-1 ---------------------------------------------------------------------
-  best = lane < kCluster ? s_cv[lane] : -1.f;
-  bidx = lane < kCluster ? s_ci[lane] : INT_MAX;
+  // ---- final top-1 (rank 0 holds the per-CTA partial maxima; in NMS mode it only seeds an empty candidate list) ----------------------
+  if (rank == 0) {
+    best = lane < kCluster ? s_cv[lane] : -1.f;
+    bidx = lane < kCluster ? s_ci[lane] : INT_MAX;
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) {
-    float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-    better(best, bidx, ov, oi);
+    for (int o = 4; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      better(best, bidx, ov, oi);
+    }
+    best = __shfl_sync(0xffffffffu, best, 0);
+    bidx = __shfl_sync(0xffffffffu, bidx, 0);
+    if (bidx == INT_MAX) bidx = 0;        // all-NaN objectness: defined as index 0
   }
-  best = __shfl_sync(0xffffffffu, best, 0);
-  bidx = __shfl_sync(0xffffffffu, bidx, 0);
-  if (bidx == INT_MAX) bidx = 0;        // all-NaN objectness: defined as index 0
 
   if (MODE == 0) {
     int s, local;
@@ -184,74 +187,99 @@ decode_kernel(const __grid_constant__ DecodeDev g, const NmsDev np, float* __res
     return;
   }
 
-  // ---- rank 0: NMS -------------------------------------------------------------------------------
-  int raw = s_count;
+  // ---- NMS: the whole cluster works on the image ------------------------------------------------------------------------------------
+  // 1. every CTA copies the raw candidates; 2. rank sort: the rank of a candidate = number of smaller keys (keys are unique), computed
+  // for a stride-8 slice per CTA and scattered into rank 0's `sorted`; 3. every CTA decodes the K best boxes; 4. all-pairs suppression
+  // bitmask, rows interleaved over the CTAs, written into rank 0's shared memory; 5. one warp of rank 0 runs the greedy scan over the
+  // bitmask rows of the KEPT boxes only (a suppressed box suppresses nothing) - identical to the sequential definition, without a
+  // block barrier per kept box.
+  int raw = *r0_count;                                                 // DSMEM read of rank 0's counter
   if (raw > kMaxRaw) {                  // cannot order more than kMaxRaw candidates exactly
-    if (tid == 0) out_count[b] = -raw;
+    if (rank == 0 && tid == 0) out_count[b] = -raw;
+    cluster.sync();                     // nobody leaves while a peer may still read its shared memory
     return;
   }
   if (raw == 0) {                       // nothing above the threshold: keep the top-1 alone
-    if (tid == 0)
+    if (rank == 0 && tid == 0)
       ns->keys[0] = ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(best)) << 32) | (unsigned)bidx;
     raw = 1;
-  }
-  int P = 1;
-  while (P < raw) P <<= 1;
-  for (int i = raw + tid; i < P; i += kThreads) ns->keys[i] = ~0ull;
-  __syncthreads();
-  for (int k = 2; k <= P; k <<= 1) {    // bitonic sort: (score desc, index asc)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < P; i += kThreads) {
-        int x = i ^ j;
-        if (x > i) {
-          unsigned long long a = ns->keys[i], c = ns->keys[x];
-          bool up = (i & k) == 0;
-          if ((a > c) == up) { ns->keys[i] = c; ns->keys[x] = a; }
-        }
-      }
-      __syncthreads();
-    }
+    cluster.sync();
   }
   const int K = min(raw, min(np.max_cand, kMaxCand));
-  for (int i = tid; i < K; i += kThreads) {
-    int j = (int)(ns->keys[i] & 0xFFFFFFFFu);
-    int s, local;
-    const float* row = row_ptr(g, b, j, s, local);
-    ns->box[i] = box_ltrb(g, row, s, local);
-    int c = 0;
-    float cv = -CUDART_INF_F;
-    for (int q = 6; q < g.C; ++q) {     // np.argmax over class logits: first maximum
-      float v = row[q];
-      if (v > cv) { cv = v; c = q - 6; }
+  if (rank != 0)
+    for (int i = tid; i < raw; i += kThreads) ns->keys[i] = r0_keys[i];
+  __syncthreads();
+  {
+    unsigned long long* r0_sorted = cluster.map_shared_rank(ns->sorted, 0);
+    for (int i = rank + kCluster * tid; i < raw; i += kCluster * kThreads) {
+      const unsigned long long key = ns->keys[i];
+      int r = 0;
+      for (int j = 0; j < raw; ++j) r += ns->keys[j] < key;             // broadcast shared-memory reads
+      if (r < K) r0_sorted[r] = key;
     }
-    ns->cls[i] = c;
   }
-  for (int i = tid; i < kMaxCand / 32; i += kThreads) {
-    int lo = i * 32;
-    ns->alive[i] = lo + 32 <= K ? 0xFFFFFFFFu : (lo >= K ? 0u : ((1u << (K - lo)) - 1u));
+  cluster.sync();                       // rank 0's `sorted` is complete
+  {
+    const unsigned long long* r0_sorted = cluster.map_shared_rank(ns->sorted, 0);
+    for (int i = tid; i < K; i += kThreads) {
+      const unsigned long long key = r0_sorted[i];
+      if (rank != 0) ns->sorted[i] = key;
+      const int j = (int)(key & 0xFFFFFFFFu);
+      int s, local;
+      const float* row = row_ptr(g, b, j, s, local);
+      ns->box[i] = box_ltrb(g, row, s, local);
+      int c = 0;
+      float cv = -CUDART_INF_F;
+      for (int q = 6; q < g.C; ++q) {     // np.argmax over class logits: first maximum
+        float v = row[q];
+        if (v > cv) { cv = v; c = q - 6; }
+      }
+      ns->cls[i] = c;
+    }
   }
   __syncthreads();
-  int nk = 0;
-  const int nblk = (K + 31) / 32;
-  for (int i = 0; i < K; ++i) {
-    if (!((ns->alive[i >> 5] >> (i & 31)) & 1u)) continue;      // block-uniform
-    if (tid == 0) ns->keep[nk] = i;
-    ++nk;
-    if (nk >= np.max_out) break;
-    float4 bi = ns->box[i];
-    int ci = ns->cls[i];
-    for (int blk = (i >> 5) + warp; blk < nblk; blk += kThreads / 32) {
-      int j = blk * 32 + lane;
-      bool sup = j > i && j < K && ns->cls[j] == ci && iou_ltrb(bi, ns->box[j]) > np.iou_thr;
-      unsigned m = __ballot_sync(0xffffffffu, sup);
-      if (lane == 0 && m) ns->alive[blk] &= ~m;
+  const int nw = (K + 31) >> 5;                                         // bitmask words per row
+  {
+    unsigned* r0_mask = cluster.map_shared_rank(ns->mask, 0);
+    const int pairs = K * nw;                                           // (row, word) pairs; row-interleaved over the CTAs
+    for (int e = tid; e < pairs; e += kThreads) {
+      const int i8 = e / nw, w = e - i8 * nw;
+      const int i = i8 * kCluster + rank;
+      if (i >= K) break;
+      unsigned m = 0;
+      if (w >= (i >> 5)) {
+        const float4 bi = ns->box[i];
+        const int ci = ns->cls[i];
+#pragma unroll 4
+        for (int t = 0; t < 32; ++t) {
+          const int j = w * 32 + t;
+          if (j > i && j < K && ns->cls[j] == ci && iou_ltrb(bi, ns->box[j]) > np.iou_thr) m |= 1u << t;
+        }
+      }
+      r0_mask[i * nw + w] = m;
     }
-    __syncthreads();
+  }
+  cluster.sync();                       // the bitmask has landed in rank 0; peers are done with remote memory
+  if (rank != 0) return;
+  __shared__ int s_nk;
+  if (warp == 0) {
+    unsigned removed = 0;               // lane l holds word l of the "suppressed" bitmap
+    int nk = 0;
+    for (int i = 0; i < K; ++i) {
+      const unsigned wv = __shfl_sync(0xffffffffu, removed, i >> 5);
+      if ((wv >> (i & 31)) & 1u) continue;                               // warp-uniform
+      if (lane == 0) ns->keep[nk] = i;
+      ++nk;
+      if (nk >= np.max_out) break;
+      if (lane < nw) removed |= ns->mask[i * nw + lane];
+    }
+    if (lane == 0) s_nk = nk;
   }
   __syncthreads();
+  const int nk = s_nk;
   for (int k = warp; k < nk; k += kThreads / 32) {
     int i = ns->keep[k];
-    unsigned long long key = ns->keys[i];
+    unsigned long long key = ns->sorted[i];
     int j = (int)(key & 0xFFFFFFFFu);
     float sc = __uint_as_float(0xFFFFFFFFu - (unsigned)(key >> 32));
     int s, local;

@@ -626,6 +626,7 @@ extern "C" int yolo_forward(yolo_handle* h, const void* input, int batch, int in
 
 extern "C" int yolo_debug_activation(yolo_handle* h, const char* layer_name, int batch, float* host_nchw, size_t n_elems) {
   if (!h || !layer_name || !host_nchw) return fail(YOLO_E_BADARG, "debug_activation: null argument");
+  if (strncmp(layer_name, "grad:", 5) == 0) return yb::train_debug_grad(h, layer_name + 5, batch, host_nchw, n_elems);
   auto it = h->named.find(layer_name);
   if (it == h->named.end()) return hfail(h, fail(YOLO_E_BADARG, "debug_activation: unknown layer '%s'", layer_name));
   const View& v = it->second;

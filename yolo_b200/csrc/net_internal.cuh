@@ -91,5 +91,7 @@ inline int hfail(yolo_handle* h, int code) {
   return code;
 }
 void train_release(yolo_handle* h, bool writeback = true);      // writeback: copy the trained parameters into the handle's own copies
+// debug: the fp32 gradient of a named activation after yolo_train_forward_backward, as NCHW (yolo_debug_activation("grad:<name>"))
+int train_debug_grad(yolo_handle* h, const char* layer_name, int batch, float* host_nchw, size_t n_elems);
 void fill_conv_desc(const yolo_handle* h, const Op& op, int batch, const void* input, void* const* outputs, ConvDesc& d);
 }  // namespace yb

@@ -720,6 +720,26 @@ static float* grad_ptr(const yolo_handle* h, const View& v) {
 }
 static __half* act16(const yolo_handle* h, const View& v) { return reinterpret_cast<__half*>(h->ws + h->bufs[v.buf].offset); }
 
+int train_debug_grad(yolo_handle* h, const char* layer_name, int batch, float* host_nchw, size_t n_elems) {
+  if (!h->train) return hfail(h, fail(YOLO_E_STATE, "debug_activation: no training state for '%s'", layer_name));
+  auto it = h->named.find(layer_name);
+  if (it == h->named.end()) return hfail(h, fail(YOLO_E_BADARG, "debug_activation: unknown layer '%s'", layer_name));
+  const View& v = it->second;
+  if (v.buf < 0) return hfail(h, fail(YOLO_E_BADARG, "debug_activation: '%s' is a user output", layer_name));
+  if (n_elems != (size_t)batch * v.C * v.H * v.W) return hfail(h, fail(YOLO_E_SHAPE, "debug_activation: '%s' is (%d,%d,%d,%d)", layer_name, batch, v.C, v.H, v.W));
+  YB_CUDA(cudaSetDevice(h->device));
+  YB_CUDA(cudaDeviceSynchronize());
+  const int pitch = grad_pitch(v);
+  std::vector<float> raw((size_t)batch * v.H * v.W * pitch);
+  YB_CUDA(cudaMemcpy(raw.data(), grad_ptr(h, v), raw.size() * 4, cudaMemcpyDeviceToHost));
+  for (int n = 0; n < batch; ++n)
+    for (int y = 0; y < v.H; ++y)
+      for (int x = 0; x < v.W; ++x)
+        for (int c = 0; c < v.C; ++c)
+          host_nchw[(((size_t)n * v.C + c) * v.H + y) * v.W + x] = raw[(((size_t)n * v.H + y) * v.W + x) * pitch + v.coff + c];
+  return YOLO_OK;
+}
+
 }  // namespace yb
 
 using namespace yb;
