@@ -31,6 +31,7 @@
  *   yolo_nccl_unique_id / yolo_train_comm_init
  *                                   <- kvstore 'device' gradient reduction inside trainer.step  car/YOLO.py:396
  *   yolo_get_param                  <- net.collect_params().save(...)  car/YOLO.py:546-549 (read-back for checkpoints)
+ *   yolo_resize_u8                  <- cv2.resize(img, size) in front of the network   car/video_node.py:150
  *   yolo_azimuth                    <- softmax + atan2 of the orientation classes   car/video_node.py:244-252, yolo_cv.py:85-94
  *   yolo_lp_corners / yolo_lp_unwarp <- ProjectRectangle6D.__call__ / add_edges    yolo_modules/licence_plate_render/__init__.py:340-402
  *   yolo_lp_loss_targets            <- _find_best_LP + _loss_mask_LP + _get_loss_LP licence_plate/LP_detection.py:259-313,354-360
@@ -205,6 +206,9 @@ int  yolo_loss_targets(const yolo_decode_geom* g, const void* const* heads, cons
  *                (ProjectRectangle6D, yolo_modules/licence_plate_render/__init__.py:340-377).
  *   lp_unwarp  : `add_edges` :379-402 - perspective crop of the frame (uint8 HWC, one frame for all plates or one per plate) to an
  *                out_h x out_w x 3 plate image per set of corners; ok[b] = 0 where the quadrilateral is degenerate (crop zero-filled). */
+/* Input stage: cv2.resize(frame, (dst_w, dst_h)) (INTER_LINEAR, OpenCV's fixed-point arithmetic: bit-exact when shrinking) for uint8 HWC
+ * device frames (B,src_h,src_w,3) -> (B,dst_h,dst_w,3); the result feeds yolo_forward(YOLO_IN_NHWC_U8) (car/video_node.py:150). */
+int  yolo_resize_u8(const unsigned char* src, int batch, int src_h, int src_w, unsigned char* dst, int dst_h, int dst_w, void* stream);
 int  yolo_azimuth(const float* rows, int batch, int row_len, int n_class, float* out_angle, float* out_radius, void* stream);
 int  yolo_lp_corners(const float* poses, int batch, int pose_stride, int pose_offset, const double intrinsics[4], float x_scale,
                      float y_scale, float* out_corners, void* stream);

@@ -66,3 +66,23 @@ def test_yolo_dense_predict():
     opred, oidx = decode.predict(spec, [ref], steps=[32], return_index=True)
     np.testing.assert_array_equal(idx, oidx)
     np.testing.assert_allclose(pred[:, :5], opred[:, :5], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("src,dst", [((480, 640), (320, 512)), ((720, 1280), (416, 416)), ((1080, 1920), (608, 608)), ((320, 512), (320, 512))])
+def test_resize_matches_cv2_bit_exact_when_shrinking(src, dst):
+    import cv2
+    import yolo_b200
+    rng = np.random.default_rng(2)
+    imgs = rng.integers(0, 256, size=(2,) + src + (3,), dtype=np.uint8)
+    got = yolo_b200.resize_u8(imgs, dst).cpu().numpy()
+    for b in range(2):
+        assert np.array_equal(got[b], cv2.resize(imgs[b], (dst[1], dst[0])))
+
+
+def test_resize_enlarging_is_within_one_level():
+    import cv2
+    import yolo_b200
+    img = np.random.default_rng(3).integers(0, 256, size=(300, 400, 3), dtype=np.uint8)
+    got = yolo_b200.resize_u8(img, (416, 416)).cpu().numpy()[0]
+    d = np.abs(got.astype(int) - cv2.resize(img, (416, 416)).astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 2e-3

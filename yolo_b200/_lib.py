@@ -79,6 +79,7 @@ SYMBOLS = {
     "yolo_decode_lp": (_I, [_VP, _I, _I, _I, _I, _I, C.POINTER(C.c_float * 3), _VP, _VP, _VP]),
     "yolo_loss_scratch_bytes": (_SZ, [_I, _I]),
     "yolo_loss_targets": (_I, [C.POINTER(DecodeGeom), C.POINTER(_VP), _VP, _I, _I, C.POINTER(LossParams), _VP, _VP, C.POINTER(_VP), _VP, _VP]),
+    "yolo_resize_u8": (_I, [_VP, _I, _I, _I, _VP, _I, _I, _VP]),
     "yolo_azimuth": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP]),
     "yolo_lp_corners": (_I, [_VP, _I, _I, _I, C.POINTER(C.c_double * 4), C.c_float, C.c_float, _VP, _VP]),
     "yolo_lp_unwarp": (_I, [_VP, _I, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP]),

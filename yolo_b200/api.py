@@ -330,6 +330,26 @@ def decode_lp(lp, mode, r_max):
     return rows, idx
 
 
+def resize_u8(frames, size):
+    """``cv2.resize(frame, (W, H))`` (bilinear, OpenCV's fixed-point arithmetic) on the GPU: frames (B,h,w,3) / (h,w,3) uint8 (numpy or
+    cuda tensor), size = (H, W) like spec['size'] -> cuda uint8 (B,H,W,3), ready for ``Net.forward`` (car/video_node.py:150)."""
+    lib = _lib.load()
+    t = _as_tensor(frames)
+    t = torch.as_tensor(t)
+    if t.dim() == 3:
+        t = t[None]
+    if not t.is_cuda:
+        t = t.cuda()
+    t = t.contiguous()
+    if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[-1] != 3:
+        raise ValueError("frames must be uint8 (B,h,w,3)")
+    out = torch.empty((t.shape[0], int(size[0]), int(size[1]), 3), dtype=torch.uint8, device=t.device)
+    with torch.cuda.device(t.device):
+        check(lib.yolo_resize_u8(C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1], t.shape[2], C.c_void_p(out.data_ptr()), out.shape[1], out.shape[2],
+                                 _stream_ptr(t.device)))
+    return out
+
+
 def azimuth(rows, n_class=24):
     """car/video_node.py:244-252 / yolo_cv.cls2ang: rows (B,C) cuda fp32 from decode_top1 -> (angle (B,), radius (B,)) cuda fp32."""
     lib = _lib.load()
