@@ -320,8 +320,8 @@ def secondary_configs(local, pk):
     except Exception as e:          # noqa: BLE001
         out["cfg1_single_frame_416"] = {"error": repr(e)[:300]}
     try:     # ---- cfg3: LPDenseNet v2 320x512 batch 64 ----
-        spec = {"size": [320, 512], "num_init_features": 32, "growth_rate": 12, "block_config": [6, 12, 24, 16], "bn_size": 4,
-                "LP_slice_point": [1, 3, 4, 7, 10], "LP_r_max": [45.0, 45.0, 30.0], "LP_num_class": 3}
+        spec = {"size": [320, 512], "num_init_features": 64, "growth_rate": 16, "block_config": [6, 12, 24, 16], "bn_size": 4,
+                "LP_slice_point": [1, 3, 4, 7, 10], "LP_r_max": [45.0, 60.0, 45.0], "LP_num_class": 3}       # licence_plate/v2/spec.yaml
         B = 64
         lp = yolo_b200.LicencePlateDetectioin(spec=spec, precision="fp16x3", max_batch=B, gpu=local)
         lp.net.load_params(synth.random_params(lp.net.param_shapes(), seed=5))

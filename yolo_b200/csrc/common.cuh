@@ -67,6 +67,10 @@ struct ConvDesc {
 int launch_conv_simt(const ConvDesc& d, int in_layout, cudaStream_t st);
 bool stem_eligible(const ConvDesc& d, int in_layout);          // dedicated 3x3 kernel for the 3-channel network input
 int launch_stem(const ConvDesc& d, int in_layout, cudaStream_t st);
+// y[c] = relu(x[c]*scale[c] + shift[c]) for c < C, 0 for C <= c < Cpad (DenseNet pre-activation BN -> ReLU, materialised once per layer so
+// that the convolution behind it is a plain tensor-core convolution); 16-bit plane formats, C % 8 == 0
+int launch_preact(const void* in, void* out, int dtype, long long pixels, int C, int Cpad, int in_cpitch, int in_coff, long long in_plane_stride,
+                  int out_cpitch, long long out_plane_stride, const float* scale, const float* shift, int* sat_flag, cudaStream_t st);
 int launch_pool(const void* in, void* out, int dtype, int N, int H, int W, int C, int in_cpitch, int in_coff,
                 long long in_plane_stride, int out_cpitch, int out_coff, long long out_plane_stride, int k, int stride, int pad,
                 int is_max, cudaStream_t st);

@@ -603,4 +603,50 @@ int launch_pool(const void* in, void* out, int dtype, int N, int H, int W, int C
   return YOLO_OK;
 }
 
+// ---- DenseNet pre-activation (BN -> ReLU) as its own pass ---------------------------------------------------------------------------
+// In a dense block every layer applies ITS OWN BatchNorm to the shared concatenated features, so the activation cannot be folded into
+// the producer's epilogue.  The FFMA kernel applies it while gathering; the tensor-core kernel stages raw tiles by TMA, so the
+// pre-activated input is materialised once per layer (channel-padded to the K step with zeros) and the convolution runs unmodified.
+template <class F>
+__global__ void __launch_bounds__(256)
+preact_kernel(const typename F::T* __restrict__ in, typename F::T* __restrict__ out, long long pixels, int C, int Cpad, int in_cpitch, int in_coff,
+              long long in_ps, int out_cpitch, long long out_ps, const float* __restrict__ scale, const float* __restrict__ shift, int* sat_flag) {
+  const int oct = Cpad >> 3;
+  const long long total = pixels * oct;
+  int sat = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / oct;
+    const int c = (int)(i - m * oct) * 8;
+    float v[8];
+    if (c < C) {
+      load8f<F>(in + m * in_cpitch + in_coff + c, in_ps, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], __ldg(scale + c + j), __ldg(shift + c + j)), 0.f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    store4f<F>(out + m * out_cpitch + c, out_ps, v, sat);
+    store4f<F>(out + m * out_cpitch + c + 4, out_ps, v + 4, sat);
+  }
+  if (sat && sat_flag) atomicOr(sat_flag, YOLO_SAT_ACT_FFMA);
+}
+
+int launch_preact(const void* in, void* out, int dtype, long long pixels, int C, int Cpad, int in_cpitch, int in_coff, long long in_plane_stride,
+                  int out_cpitch, long long out_plane_stride, const float* scale, const float* shift, int* sat_flag, cudaStream_t st) {
+  if (C % 8 || Cpad % 8 || in_cpitch % 8 || in_coff % 8 || out_cpitch % 8 || dtype == DT_F32) return fail(YOLO_E_UNSUPPORTED, "preact: needs 16-bit planes and channel counts % 8 == 0");
+  const long long total = pixels * (Cpad / 8);
+  if (total <= 0) return fail(YOLO_E_SHAPE, "preact: empty problem");
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+#define YB_PREACT(F) preact_kernel<F><<<blocks, 256, 0, st>>>(static_cast<const F::T*>(in), static_cast<F::T*>(out), pixels, C, Cpad, in_cpitch, in_coff, \
+                                                             in_plane_stride, out_cpitch, out_plane_stride, scale, shift, sat_flag)
+  if (dtype == DT_BF16) YB_PREACT(FmtBF16);
+  else if (dtype == DT_BF16X3) YB_PREACT(FmtBF16X3);
+  else YB_PREACT(FmtF16X2);
+#undef YB_PREACT
+  ++g_launches;
+  YB_CUDA(cudaGetLastError());
+  return YOLO_OK;
+}
+
 }  // namespace yb

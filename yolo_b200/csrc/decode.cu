@@ -65,6 +65,21 @@ __device__ __forceinline__ float iou_ltrb(float4 a, float4 b) {
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
 }
 
+// iou_ltrb(a, b) > thr, bit-identical to the division form: the product form decides whenever it is not within rounding distance of the
+// threshold (almost always); only then is the division evaluated.
+__device__ __forceinline__ bool iou_above(float4 a, float4 b, float thr) {
+  float il = fmaxf(a.x, b.x), it = fmaxf(a.y, b.y), ir = fminf(a.z, b.z), ib = fminf(a.w, b.w);
+  float iw = fmaxf(__fsub_rn(ir, il), 0.f), ih = fmaxf(__fsub_rn(ib, it), 0.f);
+  float inter = __fmul_rn(iw, ih);
+  if (inter <= 0.f && thr >= 0.f) return false;
+  float aa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  float ab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  float uni = __fsub_rn(__fadd_rn(aa, ab), inter);
+  float d = inter - thr * uni;
+  if (uni > 0.f && fabsf(d) > 4e-6f * fabsf(uni)) return d > 0.f;
+  return __fdiv_rn(inter, uni) > thr;
+}
+
 __device__ __forceinline__ void better(float& v, int& i, float ov, int oi) {
   if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
 }
@@ -127,15 +142,29 @@ decode_kernel(const __grid_constant__ DecodeDev g, const NmsDev np, float* __res
   const int j0 = rank * per, j1 = min(g.total, j0 + per);
   float best = -1.f;
   int bidx = INT_MAX;
-  for (int j = j0 + tid; j < j1; j += kThreads) {
-    int s, local;
-    const float* row = row_ptr(g, b, j, s, local);
-    float sc = sigmoid_exact(__ldg(row));
-    if (sc > best) { best = sc; bidx = j; }
-    if (MODE == 1 && sc > np.score_thr) {
-      int slot = atomicAdd(r0_count, 1);
-      if (slot < kMaxRaw)
-        r0_keys[slot] = ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(sc)) << 32) | (unsigned)j;
+  for (int jb = j0; jb < j1; jb += kThreads) {            // uniform trip count: the warp stays converged for the ballot below
+    const int j = jb + tid;
+    float sc = -1.f;
+    if (j < j1) {
+      int s, local;
+      const float* row = row_ptr(g, b, j, s, local);
+      sc = sigmoid_exact(__ldg(row));
+      if (sc > best) { best = sc; bidx = j; }
+    }
+    if (MODE == 1) {
+      // candidates above the threshold are appended to rank 0's list: ONE remote atomic per warp and iteration (warp-aggregated),
+      // not one per candidate - the serialised DSMEM atomics were the longest phase at ~1000 candidates per image
+      const bool cand = j < j1 && sc > np.score_thr;
+      const unsigned m = __ballot_sync(0xffffffffu, cand);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(r0_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        const int slot = base + __popc(m & ((1u << lane) - 1u));
+        if (cand && slot < kMaxRaw)
+          r0_keys[slot] = ((unsigned long long)(0xFFFFFFFFu - __float_as_uint(sc)) << 32) | (unsigned)j;
+      }
     }
   }
 #pragma unroll
@@ -253,7 +282,7 @@ decode_kernel(const __grid_constant__ DecodeDev g, const NmsDev np, float* __res
 #pragma unroll 4
         for (int t = 0; t < 32; ++t) {
           const int j = w * 32 + t;
-          if (j > i && j < K && ns->cls[j] == ci && iou_ltrb(bi, ns->box[j]) > np.iou_thr) m |= 1u << t;
+          if (j > i && j < K && ns->cls[j] == ci && iou_above(bi, ns->box[j], np.iou_thr)) m |= 1u << t;
         }
       }
       r0_mask[i * nw + w] = m;
@@ -277,15 +306,21 @@ decode_kernel(const __grid_constant__ DecodeDev g, const NmsDev np, float* __res
   }
   __syncthreads();
   const int nk = s_nk;
-  for (int k = warp; k < nk; k += kThreads / 32) {
-    int i = ns->keep[k];
-    unsigned long long key = ns->sorted[i];
-    int j = (int)(key & 0xFFFFFFFFu);
-    float sc = __uint_as_float(0xFFFFFFFFu - (unsigned)(key >> 32));
-    int s, local;
-    const float* row = row_ptr(g, b, j, s, local);
-    write_row(g, row, sc, ns->box[i], out_rows + ((size_t)b * np.max_out + k) * g.C, lane, 32);
-    if (lane == 0) out_idx[(size_t)b * np.max_out + k] = j;
+  for (int e = tid; e < nk * g.C; e += kThreads) {                     // (kept box, channel) pairs: independent loads in flight
+    const int k = e / g.C, c = e - k * g.C;
+    const int i = ns->keep[k];
+    const unsigned long long key = ns->sorted[i];
+    const int j = (int)(key & 0xFFFFFFFFu);
+    const float4 box = ns->box[i];
+    float v;
+    if (c == 0) v = __uint_as_float(0xFFFFFFFFu - (unsigned)(key >> 32));
+    else if (c == 1) v = __fmul_rn(__fadd_rn(box.y, box.w), 0.5f);
+    else if (c == 2) v = __fmul_rn(__fadd_rn(box.x, box.z), 0.5f);
+    else if (c == 3) v = __fsub_rn(box.w, box.y);
+    else if (c == 4) v = __fsub_rn(box.z, box.x);
+    else { int s, local; v = row_ptr(g, b, j, s, local)[c]; }
+    out_rows[((size_t)b * np.max_out + k) * g.C + c] = v;
+    if (c == 0) out_idx[(size_t)b * np.max_out + k] = j;
   }
   if (tid == 0) out_count[b] = nk;
 }

@@ -114,15 +114,16 @@ struct Builder {
   // or a user output); its H/W must match the (possibly upsampled) result.
   View conv(const std::string& act_name, const std::string& wname, const View& in, int cout, int k, int pad, int stride,
             int act, const std::string& bn, const std::string& bias, const std::string& prebn, const View* dst = nullptr,
-            const View* res = nullptr, int upsample2 = 0, int out_nchw = 0) {
+            const View* res = nullptr, int upsample2 = 0, int out_nchw = 0, int cin_real = 0) {
     Op op;
     op.kind = OP_CONV;
     op.name = act_name;
     op.in = in;
+    op.cin_real = cin_real > 0 ? cin_real : in.C;
     op.kh = op.kw = k; op.pad = pad; op.stride = stride; op.cout = cout; op.act = act;
     op.upsample2 = upsample2; op.out_nchw = out_nchw;
     if (!prebn.empty()) op.p_prebn = add_bn(prebn, in.C);
-    op.p_weight = add_param(wname + ".weight", {cout, in.C, k, k});
+    op.p_weight = add_param(wname + ".weight", {cout, op.cin_real, k, k});
     if (!bias.empty()) op.p_bias = add_param(bias + ".bias", {cout});
     if (!bn.empty()) op.p_bn = add_bn(bn, cout);
     int Ho = (in.H + 2 * pad - k) / stride + 1, Wo = (in.W + 2 * pad - k) / stride + 1;
@@ -136,7 +137,7 @@ struct Builder {
       op.out = new_buffer(Hd, Wd, cout, h->act_dtype, il);
     }
     if (res) { op.res = *res; op.has_res = true; }
-    h->flops_per_image += 2.0 * Ho * Wo * (double)cout * k * k * in.C;
+    h->flops_per_image += 2.0 * Ho * Wo * (double)cout * k * k * op.cin_real;
     h->ops.push_back(op);
     if (!act_name.empty() && !upsample2) h->named[act_name] = h->ops.back().out;
     return h->ops.back().out;
@@ -159,6 +160,25 @@ struct Builder {
     if (!name.empty()) h->named[name] = h->ops.back().out;
     return h->ops.back().out;
   }
+  // DenseNet pre-activation convolution: BN(prebn) -> ReLU -> conv.  With a 16-bit activation format the BN -> ReLU is materialised by its
+  // own pass into `scratch` (channels zero-padded to a multiple of 64) and the convolution runs on the tensor cores with zero-padded
+  // weights; otherwise the FFMA kernel applies the prologue while gathering.
+  View preact_conv(const std::string& wname, const View& in, View& scratch, int cout, int k, int pad, int act, const std::string& bn,
+                   const std::string& bias, const std::string& prebn, const View* dst = nullptr) {
+    const bool tc = h->act_dtype != DT_F32 && in.C % 8 == 0 && in.cpitch % 8 == 0 && in.coff % 8 == 0 && scratch.buf >= 0;
+    if (!tc) return conv("", wname, in, cout, k, pad, 1, act, bn, bias, prebn, dst);
+    const int cpad = (in.C + 63) & ~63;
+    Op op;
+    op.kind = OP_PREACT;
+    op.in = in;
+    op.out = scratch;
+    op.out.C = cpad;
+    op.cout = cpad;
+    op.p_prebn = add_bn(prebn, in.C);
+    h->ops.push_back(op);
+    return conv("", wname, h->ops.back().out, cout, k, pad, 1, act, bn, bias, "", dst, nullptr, 0, 0, in.C);
+  }
+
   // gluoncv YOLODetectionBlockV3(c): returns route, sets tip
   View detection_block(const std::string& name, View x, int c, View* tip) {
     for (int i = 0; i < 2; ++i) {
@@ -292,13 +312,19 @@ struct Builder {
     View blk = new_buffer((x.H + 2 - 3) / 2 + 1, (x.W + 2 - 3) / 2 + 1, nf + s.block_config[0] * g, dt);
     View dst = slice(blk, 0, nf);
     pool("stem.pool", x, 3, 2, 1, 1, &dst);
+    auto scratch_for = [&](const View& like, int cmax) {             // pre-activated copy of the widest layer input at this resolution
+      View none;
+      if (dt == DT_F32) return none;
+      return new_buffer(like.H, like.W, (cmax + 63) & ~63, dt);
+    };
     for (int b = 1; b <= s.n_blocks; ++b) {
       const int nlay = s.block_config[b - 1];
       int cur = nf;
+      View scratch = scratch_for(blk, nf + nlay * g);
       for (int l = 0; l < nlay; ++l) {
         const std::string p = "block" + std::to_string(b) + ".layer" + std::to_string(l);
         View xin = slice(blk, 0, cur);
-        View y = conv("", p + ".conv1", xin, s.bn_size * g, 1, 0, 1, ACT_RELU, p + ".bn2", "", p + ".bn1");
+        View y = preact_conv(p + ".conv1", xin, scratch, s.bn_size * g, 1, 0, ACT_RELU, p + ".bn2", "", p + ".bn1");
         View d2 = slice(blk, cur, g);
         conv("", p + ".conv2", y, g, 3, 1, 1, ACT_NONE, "", "", "", &d2);
         cur += g;
@@ -308,16 +334,19 @@ struct Builder {
       if (b != s.n_blocks) {
         const std::string p = "trans" + std::to_string(b);
         View xin = slice(blk, 0, nf);
-        View y = conv("", p + ".conv", xin, nf / 2, 1, 0, 1, ACT_NONE, "", "", p + ".bn");
+        View y = preact_conv(p + ".conv", xin, scratch, nf / 2, 1, 0, ACT_NONE, "", "", p + ".bn");
         nf = nf / 2;
         View nb = new_buffer(y.H / 2, y.W / 2, nf + s.block_config[b] * g, dt);
         View d2 = slice(nb, 0, nf);
         pool(p, y, 2, 2, 0, 0, &d2);
         blk = nb;
+      } else {
+        View xin = slice(blk, 0, nf);
+        View t = preact_conv("tail.conv1", xin, scratch, 512, 3, 1, ACT_RELU, "tail.bn2", "tail.conv1", "tail.bn1");
+        blk = t;                                                       // carried out of the loop below
       }
     }
-    View xin = slice(blk, 0, nf);
-    View t = conv("", "tail.conv1", xin, 512, 3, 1, 1, ACT_RELU, "tail.bn2", "tail.conv1", "tail.bn1");
+    View t = blk;
     const int nout = dense_yolo ? s.n_anchors * s.channels_per_anchor : 7 + s.lp_num_class;
     if (dense_yolo && (s.n_anchors < 1 || s.n_anchors > YOLO_MAX_ANCHORS || s.channels_per_anchor < 6)) return fail(YOLO_E_BADARG, "spec: CarDenseNet anchors/channels invalid");
     View o;
@@ -466,6 +495,7 @@ extern "C" int yolo_finalize_params(yolo_handle* h, void* stream) {
   std::vector<Slot> slots(h->ops.size());
   for (size_t i = 0; i < h->ops.size(); ++i) {
     Op& op = h->ops[i];
+    if (op.kind == OP_PREACT) { slots[i].ps = take(op.in.C); slots[i].pb = take(op.in.C); continue; }
     if (op.kind != OP_CONV) continue;
     op.cout_pad = (op.cout + 3) & ~3;
     size_t K = (size_t)op.kh * op.kw * op.in.C;
@@ -488,15 +518,26 @@ extern "C" int yolo_finalize_params(yolo_handle* h, void* stream) {
   char* dbase = static_cast<char*>(h->dparams);
   for (size_t i = 0; i < h->ops.size(); ++i) {
     Op& op = h->ops[i];
+    if (op.kind == OP_PREACT) {                // folded BatchNorm of the DenseNet pre-activation pass
+      std::vector<float> sc, sh;
+      bn_fold(h, op.p_prebn, op.in.C, sc, sh);
+      memcpy(stagev.data() + slots[i].ps / 4, sc.data(), op.in.C * 4);
+      memcpy(stagev.data() + slots[i].pb / 4, sh.data(), op.in.C * 4);
+      op.pre_scale = reinterpret_cast<float*>(dbase + slots[i].ps);
+      op.pre_shift = reinterpret_cast<float*>(dbase + slots[i].pb);
+      continue;
+    }
     if (op.kind != OP_CONV) continue;
-    const int cin = op.in.C, cout = op.cout, kh = op.kh, kw = op.kw;
-    const float* W = h->params[op.p_weight].host.data();     // OIHW
+    // cin = channels of the tensor the kernel reads; a convolution behind a pre-activation pass reads a channel-padded copy: its
+    // weights are zero-padded from cin_real to cin
+    const int cin = op.in.C, creal = op.cin_real, cout = op.cout, kh = op.kh, kw = op.kw;
+    const float* W = h->params[op.p_weight].host.data();     // OIHW, I = creal
     float* wd = stagev.data() + slots[i].w / 4;
     for (int o = 0; o < cout; ++o)
-      for (int c = 0; c < cin; ++c)
+      for (int c = 0; c < creal; ++c)
         for (int r = 0; r < kh; ++r)
           for (int s2 = 0; s2 < kw; ++s2)
-            wd[((size_t)(r * kw + s2) * cin + c) * op.cout_pad + o] = W[(((size_t)o * cin + c) * kh + r) * kw + s2];
+            wd[((size_t)(r * kw + s2) * cin + c) * op.cout_pad + o] = W[(((size_t)o * creal + c) * kh + r) * kw + s2];
     op.w_f32 = op.w_f32_own = reinterpret_cast<float*>(dbase + slots[i].w);
     std::vector<float> sc, sh;
     op.scale = op.shift = op.pre_scale = op.pre_shift = nullptr;
@@ -529,7 +570,16 @@ extern "C" int yolo_finalize_params(yolo_handle* h, void* stream) {
   // tensor-core path: pack bf16 weights (needs the host weights) - maps are built in set_workspace
   for (auto& op : h->ops) {
     if (op.kind != OP_CONV) continue;
-    int rc = umma_prepare_weights(op.umma, h->spec.precision, h->params[op.p_weight].host.data(), op.cout, op.in.C, op.kh, op.kw,
+    const float* W = h->params[op.p_weight].host.data();
+    std::vector<float> wpad;
+    if (op.cin_real != op.in.C) {              // zero-pad the input-channel dimension
+      wpad.assign((size_t)op.cout * op.in.C * op.kh * op.kw, 0.f);
+      const size_t khw = (size_t)op.kh * op.kw;
+      for (int o = 0; o < op.cout; ++o)
+        memcpy(&wpad[(size_t)o * op.in.C * khw], W + (size_t)o * op.cin_real * khw, (size_t)op.cin_real * khw * 4);
+      W = wpad.data();
+    }
+    int rc = umma_prepare_weights(op.umma, h->spec.precision, W, op.cout, op.in.C, op.kh, op.kw,
                                   op.stride, op.pad, op.in.dtype, op.pre_scale != nullptr, op.out_nchw, op.in.il, st);
     if (rc) return hfail(h, rc);
   }
@@ -606,7 +656,10 @@ extern "C" int yolo_forward(yolo_handle* h, const void* input, int batch, int in
   const int launches0 = g_launches;
   for (auto& op : h->ops) {
     int rc;
-    if (op.kind == OP_POOL) {
+    if (op.kind == OP_PREACT) {
+      rc = launch_preact(resolve(h, op.in, input, outputs), resolve(h, op.out, input, outputs), op.in.dtype, (long long)batch * op.in.H * op.in.W,
+                         op.in.C, op.out.C, op.in.cpitch, op.in.coff, op.in.ps, op.out.cpitch, op.out.ps, op.pre_scale, op.pre_shift, h->d_flags, st);
+    } else if (op.kind == OP_POOL) {
       rc = launch_pool(resolve(h, op.in, input, outputs), resolve(h, op.out, input, outputs), op.in.dtype, batch, op.in.H, op.in.W,
                        op.in.C, op.in.cpitch, op.in.coff, op.in.ps, op.out.cpitch, op.out.coff, op.out.ps, op.kh, op.stride, op.pad,
                        op.is_max, st);

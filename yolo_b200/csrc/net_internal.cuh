@@ -36,7 +36,7 @@ struct View {              // NHWC tensor or a channel slice of a wider buffer (
   bool il = false;         // planes interleaved per pixel: row = [plane 0 (C) | plane 1 (C)], cpitch = 2C, ps = C (32-channel fp16x2 tensors)
 };
 
-enum OpKind { OP_CONV = 0, OP_POOL = 1 };
+enum OpKind { OP_CONV = 0, OP_POOL = 1, OP_PREACT = 2 };   // PREACT: y = relu(bn(x)) into a zero-padded copy (DenseNet pre-activation)
 
 struct Op {
   int kind = OP_CONV;
@@ -45,6 +45,7 @@ struct Op {
   bool has_res = false;
   int kh = 1, kw = 1, stride = 1, pad = 0, cout = 0, act = ACT_NONE;
   int upsample2 = 0, out_nchw = 0, is_max = 0;
+  int cin_real = 0;        // conv reading a channel-padded pre-activated copy: the convolution's true Cin (weights are zero-padded to in.C)
   int p_weight = -1, p_bias = -1, p_bn = -1, p_prebn = -1;   // index of the FIRST param of each group
   // device parameter pointers (valid after finalize)
   float* w_f32 = nullptr;
