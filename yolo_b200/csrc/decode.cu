@@ -257,11 +257,27 @@ decode_kernel(const __grid_constant__ DecodeDev g, const NmsDev np, float* __res
       int s, local;
       const float* row = row_ptr(g, b, j, s, local);
       ns->box[i] = box_ltrb(g, row, s, local);
+      // np.argmax over the class logits (first maximum); the row is read with independent 8-byte loads first (rows are 8-byte aligned
+      // when C is even) so that their latencies overlap instead of one dependent load per compare
       int c = 0;
       float cv = -CUDART_INF_F;
-      for (int q = 6; q < g.C; ++q) {     // np.argmax over class logits: first maximum
-        float v = row[q];
-        if (v > cv) { cv = v; c = q - 6; }
+      if ((g.C & 1) == 0 && g.C <= 96) {
+        float2 r2[48];
+#pragma unroll
+        for (int q = 0; q < 48; ++q)
+          if (2 * q < g.C) r2[q] = __ldg(reinterpret_cast<const float2*>(row) + q);
+#pragma unroll
+        for (int q = 3; q < 48; ++q) {
+          if (2 * q < g.C) {
+            if (r2[q].x > cv) { cv = r2[q].x; c = 2 * q - 6; }
+            if (r2[q].y > cv) { cv = r2[q].y; c = 2 * q + 1 - 6; }
+          }
+        }
+      } else {
+        for (int q = 6; q < g.C; ++q) {
+          float v = row[q];
+          if (v > cv) { cv = v; c = q - 6; }
+        }
       }
       ns->cls[i] = c;
     }
@@ -292,11 +308,16 @@ decode_kernel(const __grid_constant__ DecodeDev g, const NmsDev np, float* __res
   if (rank != 0) return;
   __shared__ int s_nk;
   if (warp == 0) {
-    unsigned removed = 0;               // lane l holds word l of the "suppressed" bitmap
+    unsigned removed = lane < nw ? 0u : 0xFFFFFFFFu;   // lane l holds word l of the "suppressed" bitmap (bits >= K count as suppressed)
+    if (lane == nw - 1 && (K & 31)) removed |= ~((1u << (K & 31)) - 1u);
     int nk = 0;
-    for (int i = 0; i < K; ++i) {
-      const unsigned wv = __shfl_sync(0xffffffffu, removed, i >> 5);
-      if ((wv >> (i & 31)) & 1u) continue;                               // warp-uniform
+    int w = 0;                          // current word; candidates before it are decided
+    unsigned done = 0;                  // bits of word w already visited
+    while (w < nw) {
+      const unsigned alive = ~(__shfl_sync(0xffffffffu, removed, w) | done);
+      if (!alive) { ++w; done = 0; continue; }                         // warp-uniform: jump over suppressed runs 32 at a time
+      const int bit = __ffs(alive) - 1, i = w * 32 + bit;
+      done |= (bit == 31) ? 0xFFFFFFFFu : ((2u << bit) - 1u);
       if (lane == 0) ns->keep[nk] = i;
       ++nk;
       if (nk >= np.max_out) break;

@@ -123,13 +123,13 @@ lp_unwarp_kernel(const unsigned char* __restrict__ img, int img_batch_stride, in
 // < 0.1 % of the values when enlarging).  One thread per output pixel (3 channels).
 __global__ void __launch_bounds__(256)
 resize_u8_kernel(const unsigned char* __restrict__ src, int sh, int sw, unsigned char* __restrict__ dst, int dh, int dw, int batch,
-                 float scale_x, float scale_y) {
+                 double scale_x, double scale_y) {
   const size_t total = (size_t)batch * dh * dw;
   for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
     const int dx = (int)(p % dw);
     const size_t t = p / dw;
     const int dy = (int)(t % dh), b = (int)(t / dh);
-    float fx = __fsub_rn(__fmul_rn((float)dx + 0.5f, scale_x), 0.5f), fy = __fsub_rn(__fmul_rn((float)dy + 0.5f, scale_y), 0.5f);
+    float fx = (float)((dx + 0.5) * scale_x - 0.5), fy = (float)((dy + 0.5) * scale_y - 0.5);       // double, then float: OpenCV's order
     int sx = (int)floorf(fx), sy = (int)floorf(fy);
     fx -= (float)sx; fy -= (float)sy;
     if (sx < 0) { sx = 0; fx = 0.f; }
@@ -162,7 +162,7 @@ extern "C" int yolo_resize_u8(const unsigned char* src, int batch, int src_h, in
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   // cv2: scale = 1 / (dsize / ssize) evaluated in double, applied in float
   const double inv_x = (double)dst_w / src_w, inv_y = (double)dst_h / src_h;
-  resize_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_h, src_w, dst, dst_h, dst_w, batch, (float)(1.0 / inv_x), (float)(1.0 / inv_y));
+  resize_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_h, src_w, dst, dst_h, dst_w, batch, 1.0 / inv_x, 1.0 / inv_y);
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
