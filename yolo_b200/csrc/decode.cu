@@ -104,14 +104,22 @@ struct NmsDev {
   int max_out, max_cand;
 };
 
+// suppression bitmask, upper triangle only: row i keeps the words w >= i/32 (bits j > i), packed row after row
+constexpr int kMaskWords = kMaxCand * (kMaxCand / 32) - 32 * ((kMaxCand / 32) * (kMaxCand / 32 - 1) / 2);      // 16896 for 1024 candidates
+__device__ __forceinline__ int mask_row_offset(int i, int nw) {
+  const int g = i >> 5;
+  return i * nw - (32 * (g * (g - 1) / 2) + (i - 32 * g) * g);
+}
 struct NmsSmem {
-  unsigned long long keys[kMaxRaw];      // raw candidates (rank 0 gathers them; every CTA takes a copy)
   unsigned long long sorted[kMaxCand];   // the best K candidates in (score desc, index asc) order
   float4 box[kMaxCand];
-  int cls[kMaxCand];
-  int keep[kMaxCand];
-  unsigned mask[kMaxCand * (kMaxCand / 32)];   // rank 0: bit j of row i = "i suppresses j" (j > i, same class, IoU > thr)
-};
+  unsigned short cls[kMaxCand];
+  unsigned short keep[kMaxCand];
+  union {                                // the raw candidate list is dead once the rank sort has run: the bitmask reuses its space
+    unsigned long long keys[kMaxRaw];    // raw candidates (rank 0 gathers them; every CTA takes a copy)
+    unsigned mask[kMaskWords];           // rank 0: bit j of row i = "i suppresses j" (j > i, same class, IoU > thr)
+  };
+};                                       // 96 KB: two CTAs per SM, so the 8 x batch CTAs of 32 images run in one wave
 
 template <int MODE>   // 0 = top-1 (reference semantics), 1 = NMS extension
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads)
@@ -279,29 +287,29 @@ decode_kernel(const __grid_constant__ DecodeDev g, const NmsDev np, float* __res
           if (v > cv) { cv = v; c = q - 6; }
         }
       }
-      ns->cls[i] = c;
+      ns->cls[i] = (unsigned short)c;
     }
   }
   __syncthreads();
   const int nw = (K + 31) >> 5;                                         // bitmask words per row
   {
     unsigned* r0_mask = cluster.map_shared_rank(ns->mask, 0);
-    const int pairs = K * nw;                                           // (row, word) pairs; row-interleaved over the CTAs
+    // (row, word) pairs of this CTA's rows i = rank, rank + 8, ...; the threads of a warp share the WORD and differ in the row, so the
+    // candidate-side loads (cls[j], box[j]) are shared-memory broadcasts instead of 32-way bank conflicts
+    const int R = (K - rank + kCluster - 1) / kCluster;
+    const int pairs = R > 0 ? R * nw : 0;
     for (int e = tid; e < pairs; e += kThreads) {
-      const int i8 = e / nw, w = e - i8 * nw;
-      const int i = i8 * kCluster + rank;
-      if (i >= K) break;
+      const int w = e / R, i = (e - w * R) * kCluster + rank;
+      if (w < (i >> 5)) continue;                                       // lower triangle: not stored
       unsigned m = 0;
-      if (w >= (i >> 5)) {
-        const float4 bi = ns->box[i];
-        const int ci = ns->cls[i];
+      const float4 bi = ns->box[i];
+      const int ci = ns->cls[i];
 #pragma unroll 4
-        for (int t = 0; t < 32; ++t) {
-          const int j = w * 32 + t;
-          if (j > i && j < K && ns->cls[j] == ci && iou_above(bi, ns->box[j], np.iou_thr)) m |= 1u << t;
-        }
+      for (int t = 0; t < 32; ++t) {
+        const int j = w * 32 + t;
+        if (j > i && j < K && ns->cls[j] == ci && iou_above(bi, ns->box[j], np.iou_thr)) m |= 1u << t;
       }
-      r0_mask[i * nw + w] = m;
+      r0_mask[mask_row_offset(i, nw) + w - (i >> 5)] = m;
     }
   }
   cluster.sync();                       // the bitmask has landed in rank 0; peers are done with remote memory
@@ -321,7 +329,7 @@ decode_kernel(const __grid_constant__ DecodeDev g, const NmsDev np, float* __res
       if (lane == 0) ns->keep[nk] = i;
       ++nk;
       if (nk >= np.max_out) break;
-      if (lane < nw) removed |= ns->mask[i * nw + lane];
+      if (lane >= (i >> 5) && lane < nw) removed |= ns->mask[mask_row_offset(i, nw) + lane - (i >> 5)];
     }
     if (lane == 0) s_nk = nk;
   }

@@ -103,6 +103,7 @@ struct TrainLayer {                       // per conv op
   WgradPlan wg;
   float* wT = nullptr; int cin_pad = 0;               // FFMA data gradient (head convs): flipped fp32 weights
   bool fwd_umma = false;
+  bool dgrad_accum = true, dres_accum = true;         // false: this op is the FIRST writer of that gradient range -> plain store, no zero-fill needed
 };
 
 struct TrainState {
@@ -113,6 +114,7 @@ struct TrainState {
   size_t arena_bytes = 0;
   std::vector<size_t> gbuf_off;           // byte offset of the fp32 gradient buffer mirroring forward buffer i
   size_t grads_begin = 0, grads_bytes = 0;
+  std::vector<char> gbuf_memset;          // gradient buffers that still need zero-filling each step (first-writer analysis failed)
   void* loss_scratch = nullptr; size_t loss_scratch_bytes = 0;
   float* dheads[YOLO_MAX_SCALES + 1] = {nullptr, nullptr, nullptr, nullptr};
   float* wg_scratch = nullptr; size_t wg_scratch_bytes = 0;
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, const float* __restrict__ dy, int dy_cpitch, int dy_coff,
                      int upsample2, int Ho, int Wo, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ ab, int act, float* __restrict__ dres, int dres_cpitch,
-                     int dres_coff, double* __restrict__ slab, unsigned int* __restrict__ gmax_bits) {
+                     int dres_coff, int dres_accum, double* __restrict__ slab, unsigned int* __restrict__ gmax_bits) {
   const int cb = min(C, 256), octs = cb >> 3, lanes = 256 / octs;
   const int oc = threadIdx.x % octs, rl = threadIdx.x / octs;
   const int c = blockIdx.x * cb + oc * 8;
@@ -319,7 +321,8 @@ bn_bwd_reduce_kernel(const __half* __restrict__ z, long long z_ps, int M, int C,
         load_dy8(dy, dy_cpitch, dy_coff, upsample2, Ho, Wo, m, c, g);
         if (dres) {
           float* rp = dres + (size_t)m * dres_cpitch + dres_coff + c;
-          float4 a = *reinterpret_cast<float4*>(rp), b = *reinterpret_cast<float4*>(rp + 4);
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+          if (dres_accum) { a = *reinterpret_cast<float4*>(rp); b = *reinterpret_cast<float4*>(rp + 4); }
           a.x += g[0]; a.y += g[1]; a.z += g[2]; a.w += g[3]; b.x += g[4]; b.y += g[5]; b.z += g[6]; b.w += g[7];
           *reinterpret_cast<float4*>(rp) = a; *reinterpret_cast<float4*>(rp + 4) = b;
         }
@@ -952,6 +955,42 @@ extern "C" int yolo_train_init(yolo_handle* h, float* params_flat, float* grads_
       }
     }
   }
+  // First-writer analysis of the fp32 gradient buffers: walking the ops in backward order, the first producer of a channel range
+  // stores (no read-modify-write), later producers accumulate - and the 2.8 GB zero-fill per step disappears.  A range that is only
+  // partly covered when somebody accumulates into it, or is read before anybody wrote it, falls back to zero-filling that buffer.
+  {
+    std::vector<std::vector<std::pair<int, int>>> written(h->bufs.size());
+    T->gbuf_memset.assign(h->bufs.size(), 0);
+    auto covered = [&](int buf, int lo, int hi) {                 // is [lo, hi) inside the union of the written ranges?
+      std::vector<std::pair<int, int>> w = written[buf];
+      std::sort(w.begin(), w.end());
+      int pos = lo;
+      for (auto& r : w) { if (r.first > pos) break; pos = std::max(pos, r.second); }
+      return pos >= hi;
+    };
+    auto touches = [&](int buf, int lo, int hi) {
+      for (auto& r : written[buf]) if (r.first < hi && lo < r.second) return true;
+      return false;
+    };
+    auto write = [&](const View& v, bool& accum) {
+      const int lo = v.coff, hi = v.coff + v.C;
+      if (!touches(v.buf, lo, hi)) accum = false;
+      else { accum = true; if (!covered(v.buf, lo, hi)) T->gbuf_memset[v.buf] = 1; }
+      written[v.buf].push_back({lo, hi});
+    };
+    for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
+      const Op& op = h->ops[i];
+      TrainLayer& L = T->layers[i];
+      if (L.has_bn && op.out.buf >= 0 && !covered(op.out.buf, op.out.coff, op.out.coff + op.out.C)) T->gbuf_memset[op.out.buf] = 1;   // read before written
+      if (L.has_bn && op.has_res) write(op.res, L.dres_accum);
+      if (op.in.buf >= 0) write(op.in, L.dgrad_accum);
+    }
+    for (size_t i = 0; i < h->ops.size(); ++i) {                  // a zero-filled buffer is accumulated into by everybody
+      const Op& op = h->ops[i];
+      if (op.in.buf >= 0 && T->gbuf_memset[op.in.buf]) T->layers[i].dgrad_accum = true;
+      if (op.has_res && T->gbuf_memset[op.res.buf]) T->layers[i].dres_accum = true;
+    }
+  }
   YB_CUDA(cudaMemcpyAsync(T->P, hostP.data(), n_flat * 4, cudaMemcpyHostToDevice, st));
   YB_CUDA(cudaMemsetAsync(T->M1, 0, n_flat * 4, st));
   YB_CUDA(cudaMemsetAsync(T->M2, 0, n_flat * 4, st));
@@ -1087,7 +1126,11 @@ static int train_fwd_bwd(yolo_handle* h, const void* input, int in_layout, const
       YB_CUDA(cudaMemsetAsync(T->dheads[i], 0, (size_t)batch * v.H * v.W * v.C * 4, st));
   }
   // ---------------- backward ----------------
-  YB_CUDA(cudaMemsetAsync(T->arena + T->grads_begin, 0, T->grads_bytes, st));
+  for (size_t bi = 0; bi < h->bufs.size(); ++bi)
+    if (T->gbuf_memset[bi]) {
+      const size_t elems = h->bufs[bi].bytes_per_image / dtype_bytes_per_elem(h->bufs[bi].dtype);
+      YB_CUDA(cudaMemsetAsync(T->arena + T->gbuf_off[bi], 0, elems * (size_t)h->spec.max_batch * 4, st));
+    }
   T->reduced = false;
   size_t bucket_hi = T->n_flat;                                   // gradients of [bucket_lo, bucket_hi) are complete when the walk passes bucket_lo
   for (int i = (int)h->ops.size() - 1; i >= 0; --i) {
@@ -1106,7 +1149,7 @@ static int train_fwd_bwd(yolo_handle* h, const void* input, int in_layout, const
       const int nslab = std::max(1, std::min(std::min(L.slab_cap, kSlabCtas / ((C + cb - 1) / cb)), M / (red_lanes * 16)));
       bn_bwd_reduce_kernel<<<dim3((C + cb - 1) / cb, nslab), 256, 0, st>>>(L.z, L.z_ps, M, C, dy, dyp, op.out.coff, op.upsample2, L.Ho, L.Wo, L.mean,
                                                                          L.rstd, L.ab, op.act, dres, op.has_res ? grad_pitch(op.res) : 0, op.res.coff,
-                                                                         L.slab, reinterpret_cast<unsigned int*>(L.dzscale + 2));
+                                                                         L.dres_accum ? 1 : 0, L.slab, reinterpret_cast<unsigned int*>(L.dzscale + 2));
       bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(L.slab, nslab, M, C, L.ab, L.mg, T->G + L.o_gamma, T->G + L.o_beta,
                                                           reinterpret_cast<unsigned int*>(L.dzscale + 3));
       {
@@ -1152,13 +1195,13 @@ static int train_fwd_bwd(yolo_handle* h, const void* input, int in_layout, const
         d.sat_flag = h->d_flags;
         if (L.dgrad.enabled) {
           UmmaExtra ex;
-          ex.acc_scale_dev = L.dzscale + 1; ex.accum = 1;
+          ex.acc_scale_dev = L.dzscale + 1; ex.accum = L.dgrad_accum ? 1 : 0;
           rc = launch_conv_umma(L.dgrad, d, st, &ex);
         } else {
           d.in = L.dz; d.H = L.Ho; d.W = L.Wo; d.in_plane_stride = L.dz_plane_rows * C; d.in_dil = op.stride;      // implicit zero-dilation
           d.w_f32 = L.wT; d.cout_pad = L.cin_pad;
           d.dyn_scale = L.dzscale + 1;
-          d.res = d.out; d.res_cpitch = d.out_cpitch; d.res_coff = d.out_coff;
+          if (L.dgrad_accum) { d.res = d.out; d.res_cpitch = d.out_cpitch; d.res_coff = d.out_coff; }
           rc = launch_conv_simt(d, 0, st);
         }
         if (rc) return hfail(h, rc);
@@ -1186,7 +1229,7 @@ static int train_fwd_bwd(yolo_handle* h, const void* input, int in_layout, const
       d.w_f32 = L.wT; d.cout_pad = L.cin_pad;
       d.act = ACT_NONE;
       float* dx = grad_ptr(h, op.in);
-      d.res = dx; d.res_cpitch = grad_pitch(op.in); d.res_coff = op.in.coff;        // accumulate: several consumers may feed one tensor
+      if (L.dgrad_accum) { d.res = dx; d.res_cpitch = grad_pitch(op.in); d.res_coff = op.in.coff; }      // several consumers may feed one tensor
       d.out = dx; d.out_dtype = DT_F32; d.Ho = op.in.H; d.Wo = op.in.W; d.out_cpitch = grad_pitch(op.in); d.out_coff = op.in.coff;
       rc = launch_conv_simt(d, 0, st);
       if (rc) return hfail(h, rc);
