@@ -281,28 +281,36 @@ def _head_ptrs(heads):
     return ts, (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
 
 
-def decode_top1(spec, heads, steps=None):
-    """car/YOLO.py:568-597 as one kernel.  Returns (rows (B,C) cuda fp32, idx (B,) cuda int32)."""
+def decode_top1(spec, heads, steps=None, out=None):
+    """car/YOLO.py:568-597 as one kernel.  Returns (rows (B,C) cuda fp32, idx (B,) cuda int32); ``out=(rows, idx)`` reuses buffers."""
     lib = _lib.load()
     ts, ptrs = _head_ptrs(heads)
     B, dev = ts[0].shape[0], ts[0].device
     g = make_geom(spec, steps)
-    rows = torch.empty((B, g.channels_per_anchor), dtype=torch.float32, device=dev)
-    idx = torch.empty((B,), dtype=torch.int32, device=dev)
+    if out is not None:
+        rows, idx = out
+    else:
+        rows = torch.empty((B, g.channels_per_anchor), dtype=torch.float32, device=dev)
+        idx = torch.empty((B,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         check(lib.yolo_decode_top1(C.byref(g), ptrs, B, C.c_void_p(rows.data_ptr()), C.c_void_p(idx.data_ptr()), _stream_ptr(dev)))
     return rows, idx
 
 
-def decode_nms(spec, heads, score_thr=0.5, iou_thr=0.45, max_out=100, max_cand=1024, steps=None):
+def decode_nms(spec, heads, score_thr=0.5, iou_thr=0.45, max_out=100, max_cand=1024, steps=None, out=None):
+    """Fused decode + class-aware NMS.  Returns (rows (B,max_out,C), idx (B,max_out), count (B,)); entries beyond count[b] are 0 / -1
+    unless ``out=(rows, idx, count)`` passes caller-owned buffers (then only the first count[b] entries are defined)."""
     lib = _lib.load()
     ts, ptrs = _head_ptrs(heads)
     B, dev = ts[0].shape[0], ts[0].device
     g = make_geom(spec, steps)
     p = NmsParams(float(score_thr), float(iou_thr), int(max_out), int(max_cand))
-    rows = torch.zeros((B, max_out, g.channels_per_anchor), dtype=torch.float32, device=dev)
-    idx = torch.full((B, max_out), -1, dtype=torch.int32, device=dev)
-    cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    if out is not None:
+        rows, idx, cnt = out
+    else:
+        rows = torch.zeros((B, max_out, g.channels_per_anchor), dtype=torch.float32, device=dev)
+        idx = torch.full((B, max_out), -1, dtype=torch.int32, device=dev)
+        cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         check(lib.yolo_decode_nms(C.byref(g), ptrs, B, C.byref(p), C.c_void_p(rows.data_ptr()), C.c_void_p(idx.data_ptr()),
                                   C.c_void_p(cnt.data_ptr()), _stream_ptr(dev)))
