@@ -521,12 +521,14 @@ def run_ours(args):
                          f"tcgen05 16-bit MMA passes per fp32-grade product" if passes > 1 else f"{pk_src} bf16 sustained")
         achieved = B * flops_img / (fwd_ms / 1e3) / 1e12
         traffic, traffic_note = None, None
-        tp = os.path.join(ROOT, "profiles", f"r1_step_traffic_{precision}.json")
-        if os.path.exists(tp) and B == 32 and S == 416:
-            tj = json.load(open(tp))
-            traffic = tj["conv_launches_dram_bytes_per_step"]
-            traffic_note = ("dram__bytes_read+write summed over the conv launches of one step from a committed ncu capture "
-                            "(profiles/r1_step_traffic_%s.csv), not measured in this run" % precision)
+        for rnd in ("r2", "r1"):                                   # the newest committed capture (scripts/step_traffic.py)
+            tp = os.path.join(ROOT, "profiles", f"{rnd}_step_traffic_{precision}.json")
+            if os.path.exists(tp) and B == 32 and S == 416:
+                tj = json.load(open(tp))
+                traffic = tj["conv_launches_dram_bytes_per_step"]
+                traffic_note = ("dram__bytes_read+write summed over the conv launches of one step from a committed ncu capture "
+                                "(profiles/%s_step_traffic_%s.json), not measured in this run" % (rnd, precision))
+                break
         dec_bytes = B * sum(o.t[0].numel() for o in out) * 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),

@@ -12,7 +12,7 @@ if len(sys.argv) > 2:
     rows = rows[-int(sys.argv[2]):]
 for r in rows:
     name = r["Kernel Name"]
-    short = name[name.find("void ") + 5 if "void " in name else 0:name.find("(")]
+    short = name[5 if name.startswith("void ") else 0:name.find("(")]
     v = float(r["Metric Value"].replace(",", ""))
     unit = r["Metric Unit"]
     us = v / 1000.0 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1000.0)

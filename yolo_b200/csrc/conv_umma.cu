@@ -454,9 +454,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (p.upsample2) {
         const int img = m / HoWo, rem = m - img * HoWo;
         const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
-        npix = 4;
+        if (p.upsample2 == 1) {                             // nearest 2x upsampling: four copies
+          npix = 4;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) pix[q] = ((size_t)img * 2 * p.Ho + 2 * oh + (q >> 1)) * (2 * p.Wo) + 2 * ow + (q & 1);
+          for (int q = 0; q < 4; ++q) pix[q] = ((size_t)img * 2 * p.Ho + 2 * oh + (q >> 1)) * (2 * p.Wo) + 2 * ow + (q & 1);
+        } else {                                            // 2 + parity class: one pixel of the 2x grid (strided data gradient)
+          const int q = p.upsample2 - 2;
+          pix[0] = ((size_t)img * 2 * p.Ho + 2 * oh + (q >> 1)) * (2 * p.Wo) + 2 * ow + (q & 1);
+        }
       } else {
         pix[0] = (size_t)m;
       }
@@ -695,14 +700,14 @@ static void set_prescale(UmmaConv& u, float wmax, int top) {
 }
 
 int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int cout, int cin, int kh, int kw, int stride,
-                         int pad, int in_dtype, bool has_prologue, int out_nchw, bool in_interleaved, cudaStream_t st) {
+                         int pad, int in_dtype, bool has_prologue, int out_nchw, bool in_interleaved, cudaStream_t st, bool rect_ok) {
   u.eligible = false;
   u.enabled = false;
   u.c32i = false;
   if (precision == YOLO_PREC_FP32) return YOLO_OK;
   if (umma_env().disable) return YOLO_OK;
   // shapes the tensor-core kernel takes; everything else stays on the FFMA kernel
-  if (cin % 32 != 0 || has_prologue || out_nchw || kh != kw || in_dtype != act_dtype_of(precision)) return YOLO_OK;
+  if (cin % 32 != 0 || has_prologue || out_nchw || (kh != kw && !rect_ok) || in_dtype != act_dtype_of(precision)) return YOLO_OK;
   if (stride < 1 || stride > 8 || pad > 127) return YOLO_OK;
   if (in_interleaved && (precision != YOLO_PREC_FP16X3 || cin != 32)) return YOLO_OK;      // only the C32I kernel reads that layout
   u.c32i = in_interleaved;
@@ -787,73 +792,109 @@ __device__ __forceinline__ void split_f16(float v, unsigned short& hi, unsigned 
   hi = __half_as_ushort(h);
   lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
 }
-__global__ void __launch_bounds__(256)
-pack_fwd_kernel(const float* __restrict__ w_mat, int K, int Cin, int Cout, int cout_pad, float prescale, unsigned short* __restrict__ out,
-                int rows, int c32i, int* sat_flag) {
-  __shared__ float tile[32][33];
-  const int k0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+// One launch packs every direction of a layer: the 32 x 32 tile of w_mat is written straight into the data-gradient layout(s)
+// (`o` fastest on both sides) and through a shared-memory transpose into the forward layout.
+//
+// Parity classes of the data gradient of a 3x3 / stride 2 / pad 1 convolution: the input pixels (2a + py, 2b + px) see only the taps
+// whose row has the parity of py + 1 (py = 0: r = 1 at dz row a; py = 1: r = 2 at row a, r = 0 at row a + 1), so each class is a
+// dense kh' x kw' convolution (kh' = 1 + py, kw' = 1 + px) over dz itself - no zero-dilated copy, a quarter of the MMAs.  Every tap
+// belongs to exactly one class; packed[pl][c][tap'*Cout + o] with tap' = r'*kw' + s'.
+struct PackArgs {
+  const float* w; int K, Cin, Cout, cout_pad, kh, kw;
+  float ps_fwd, ps_dg;
+  unsigned short* out_fwd; int rows_fwd, c32i;
+  int dg_mode;                       // 0: none, 1: flipped filter, 2: parity classes
+  unsigned short* out_dg[4]; int rows_dg;
+  int* sat_flag;
+};
+__device__ __forceinline__ void split_f16_pair(float v0, float v1, uint32_t& hi, uint32_t& lo, int& sat) {
+  unsigned short h0, l0, h1, l1;
+  split_f16(v0, h0, l0, sat);
+  split_f16(v1, h1, l1, sat);
+  hi = (uint32_t)h0 | ((uint32_t)h1 << 16);
+  lo = (uint32_t)l0 | ((uint32_t)l1 << 16);
+}
+// 64 (k) x 64 (o) tiles, two elements per thread on both sides (4-byte stores; every tensor-core shape has even K and Cout)
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackArgs a) {
+  __shared__ float tile[64][65];
+  const int k0 = blockIdx.x * 64, o0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
-  for (int j = ty; j < 32; j += 8) {
-    const int k = k0 + j, o = o0 + tx;
-    tile[j][tx] = (k < K && o < Cout) ? w_mat[(size_t)k * cout_pad + o] * prescale : 0.f;
-  }
-  __syncthreads();
   int sat = 0;
-  const size_t Kp = c32i ? (size_t)(K / Cin) * 64 : (size_t)K;
-  for (int j = ty; j < 32; j += 8) {
-    const int o = o0 + j, k = k0 + tx;
-    if (o >= Cout || k >= K) continue;
-    unsigned short hi, lo;
-    split_f16(tile[tx][j], hi, lo, sat);
-    if (c32i) {
-      const int tap = k / 32, c = k - tap * 32;
-      const size_t k2 = (size_t)tap * 64 + c;
-      out[(size_t)o * Kp + k2] = hi;
-      out[(size_t)o * Kp + k2 + 32] = hi;
-      out[((size_t)rows + o) * Kp + k2] = lo;
-    } else {
-      out[(size_t)o * Kp + k] = hi;
-      out[((size_t)rows + o) * Kp + k] = lo;
+  for (int j = ty; j < 64; j += 8) {
+    const int k = k0 + j, o = o0 + 2 * tx;
+    const bool in = k < a.K && o < a.Cout;                            // Cout is even: o + 1 is inside as well
+    const float2 v = in ? *reinterpret_cast<const float2*>(a.w + (size_t)k * a.cout_pad + o) : make_float2(0.f, 0.f);
+    tile[j][2 * tx] = v.x;
+    tile[j][2 * tx + 1] = v.y;
+    if (a.dg_mode && in) {
+      const int tap = k / a.Cin, c = k - tap * a.Cin, r = tap / a.kw, s2 = tap - r * a.kw;
+      unsigned short* out;
+      size_t Kp;
+      int tap2;
+      if (a.dg_mode == 1) {
+        out = a.out_dg[0];
+        Kp = (size_t)a.kh * a.kw * a.Cout;
+        tap2 = (a.kh - 1 - r) * a.kw + (a.kw - 1 - s2);
+      } else {
+        const int py = r != 1, px = s2 != 1, kwp = 1 + px;
+        out = a.out_dg[py * 2 + px];
+        Kp = (size_t)(1 + py) * kwp * a.Cout;
+        tap2 = (r == 0 ? 1 : 0) * kwp + (s2 == 0 ? 1 : 0);
+      }
+      uint32_t hi, lo;
+      split_f16_pair(v.x * a.ps_dg, v.y * a.ps_dg, hi, lo, sat);
+      *reinterpret_cast<uint32_t*>(out + (size_t)c * Kp + (size_t)tap2 * a.Cout + o) = hi;
+      *reinterpret_cast<uint32_t*>(out + ((size_t)a.rows_dg + c) * Kp + (size_t)tap2 * a.Cout + o) = lo;
     }
   }
-  if (sat && sat_flag) atomicOr(sat_flag, YOLO_SAT_WEIGHT);
-}
-__global__ void __launch_bounds__(256)
-pack_dgrad_kernel(const float* __restrict__ w_mat, int kh, int kw, int Cin, int Cout, int cout_pad, float prescale,
-                  unsigned short* __restrict__ out, int rows, int* sat_flag) {
-  const size_t total = (size_t)kh * kw * Cin * Cout;
-  const size_t Kp = (size_t)kh * kw * Cout;
-  int sat = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int o = (int)(i % Cout);
-    const size_t t = i / Cout;
-    const int c = (int)(t % Cin);
-    const int tap = (int)(t / Cin), r = tap / kw, s = tap - r * kw;
-    const int tap2 = (kh - 1 - r) * kw + (kw - 1 - s);
-    unsigned short hi, lo;
-    split_f16(w_mat[((size_t)tap * Cin + c) * cout_pad + o] * prescale, hi, lo, sat);
-    out[(size_t)c * Kp + (size_t)tap2 * Cout + o] = hi;
-    out[((size_t)rows + c) * Kp + (size_t)tap2 * Cout + o] = lo;
+  if (a.out_fwd) {
+    __syncthreads();
+    const size_t Kp = a.c32i ? (size_t)(a.K / a.Cin) * 64 : (size_t)a.K;
+    for (int j = ty; j < 64; j += 8) {
+      const int o = o0 + j, k = k0 + 2 * tx;
+      if (o >= a.Cout || k >= a.K) continue;
+      uint32_t hi, lo;
+      split_f16_pair(tile[2 * tx][j] * a.ps_fwd, tile[2 * tx + 1][j] * a.ps_fwd, hi, lo, sat);
+      if (a.c32i) {
+        const int tap = k / 32, c = k - tap * 32;
+        const size_t k2 = (size_t)tap * 64 + c;
+        *reinterpret_cast<uint32_t*>(a.out_fwd + (size_t)o * Kp + k2) = hi;
+        *reinterpret_cast<uint32_t*>(a.out_fwd + (size_t)o * Kp + k2 + 32) = hi;
+        *reinterpret_cast<uint32_t*>(a.out_fwd + ((size_t)a.rows_fwd + o) * Kp + k2) = lo;
+      } else {
+        *reinterpret_cast<uint32_t*>(a.out_fwd + (size_t)o * Kp + k) = hi;
+        *reinterpret_cast<uint32_t*>(a.out_fwd + ((size_t)a.rows_fwd + o) * Kp + k) = lo;
+      }
+    }
   }
-  if (sat && sat_flag) atomicOr(sat_flag, YOLO_SAT_WEIGHT);
+  if (sat && a.sat_flag) atomicOr(a.sat_flag, YOLO_SAT_WEIGHT);
 }
 
 void umma_set_prescale(UmmaConv& u, float wmax, int top) { set_prescale(u, wmax, top); }
+bool umma_disabled() { return umma_env().disable; }
 
-int umma_pack_device(const UmmaConv& u, const float* w_mat, int w_cin, int w_cout, int cout_pad, bool dgrad, int* sat_flag, cudaStream_t st) {
-  if (!u.eligible) return YOLO_OK;
-  if (u.precision != YOLO_PREC_FP16X3) return fail(YOLO_E_UNSUPPORTED, "umma: device weight packing exists for fp16x3 only");
-  unsigned short* out = static_cast<unsigned short*>(u.w_packed);
-  if (!dgrad) {
-    const int K = u.kh * u.kw * w_cin;
-    dim3 grid((K + 31) / 32, (w_cout + 31) / 32);
-    pack_fwd_kernel<<<grid, 256, 0, st>>>(w_mat, K, w_cin, w_cout, cout_pad, u.prescale, out, u.rows, u.c32i ? 1 : 0, sat_flag);
-  } else {
-    const size_t total = (size_t)u.kh * u.kw * w_cin * w_cout;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    pack_dgrad_kernel<<<blocks, 256, 0, st>>>(w_mat, u.kh, u.kw, w_cin, w_cout, cout_pad, u.prescale, out, u.rows, sat_flag);
+int umma_pack_device(const UmmaConv* fwd, const UmmaConv* dg, int n_dg, const float* w_mat, int w_cin, int w_cout, int cout_pad, int kh, int kw,
+                     int* sat_flag, cudaStream_t st) {
+  PackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.w = w_mat; a.K = kh * kw * w_cin; a.Cin = w_cin; a.Cout = w_cout; a.cout_pad = cout_pad; a.kh = kh; a.kw = kw; a.sat_flag = sat_flag;
+  if (fwd && fwd->eligible) {
+    if (fwd->precision != YOLO_PREC_FP16X3) return fail(YOLO_E_UNSUPPORTED, "umma: device weight packing exists for fp16x3 only");
+    a.out_fwd = static_cast<unsigned short*>(fwd->w_packed); a.rows_fwd = fwd->rows; a.c32i = fwd->c32i ? 1 : 0; a.ps_fwd = fwd->prescale;
   }
+  if (dg && n_dg > 0 && dg[0].eligible) {
+    if (n_dg != 1 && n_dg != 4) return fail(YOLO_E_BADARG, "umma: one data-gradient convolution or four parity classes");
+    if (n_dg == 4 && (kh != 3 || kw != 3)) return fail(YOLO_E_BADARG, "umma: parity classes exist for 3x3 filters");
+    for (int q = 0; q < n_dg; ++q) {
+      if (!dg[q].eligible || dg[q].precision != YOLO_PREC_FP16X3) return fail(YOLO_E_UNSUPPORTED, "umma: device weight packing exists for fp16x3 only");
+      a.out_dg[q] = static_cast<unsigned short*>(dg[q].w_packed);
+    }
+    a.dg_mode = n_dg == 4 ? 2 : 1; a.rows_dg = dg[0].rows; a.ps_dg = dg[0].prescale;
+  }
+  if (!a.out_fwd && !a.dg_mode) return YOLO_OK;
+  if ((a.K | w_cout | cout_pad) & 1) return fail(YOLO_E_UNSUPPORTED, "umma: device weight packing needs even K and Cout");
+  dim3 grid((a.K + 63) / 64, (w_cout + 63) / 64);
+  pack_weights_kernel<<<grid, 256, 0, st>>>(a);
   ++g_launches;
   YB_CUDA(cudaGetLastError());
   return YOLO_OK;
@@ -871,7 +912,7 @@ int umma_build_maps(UmmaConv& u, void* in_base, int max_batch, int H, int W, int
   const CUtensorMapDataType dt = u.precision == YOLO_PREC_FP16X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapSwizzle sw = u.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   u.a_tiled = false;
-  if (u.kh == 1 && u.stride == 1 && u.pad == 0 && umma_env().a_tiled) {
+  if (u.kh == 1 && u.kw == 1 && u.stride == 1 && u.pad == 0 && umma_env().a_tiled) {
     // 1x1 convolution: A is the plain row-major matrix [planes*max_batch*H*W][cpitch] -> tiled map
     cuuint64_t rows = (cuuint64_t)np * max_batch * H * W;
     cuuint64_t gd[2] = {(cuuint64_t)cpitch, rows};
@@ -891,6 +932,7 @@ int umma_build_maps(UmmaConv& u, void* in_base, int max_batch, int H, int W, int
   cuuint64_t gstr[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2};
   int lower[2] = {-u.pad, -u.pad};
   int upper[2] = {u.pad - (u.kw - 1), u.pad - (u.kh - 1)};
+  if (u.pad_high_full) { upper[0] = 0; upper[1] = 0; }     // every pixel is a base pixel; taps past the far edge read zeros
   cuuint32_t estr[4] = {1, (cuuint32_t)u.stride, (cuuint32_t)u.stride, 1};
   CUresult cr = g_encode_im2col(reinterpret_cast<CUtensorMap*>(u.map_a), dt, 4, in_base, gdim, gstr, lower, upper, (cuuint32_t)u.bk, TILE_M, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

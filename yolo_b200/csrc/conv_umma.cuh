@@ -22,6 +22,7 @@ struct UmmaConv {
   bool a_tiled = false;       // 1x1 conv: map_a is a tiled 2-D map over [pixels][channels]
   long long a_plane_rows = 0;
   int max_batch = 0;
+  bool pad_high_full = false; // im2col: pad = 0 on the near edge, k-1 on the far edge (parity classes of a strided data gradient)
   bool c32i = false;          // Cin = 32, plane-interleaved activations ([hi(32) | lo(32)] per pixel): KIND 7
   float prescale = 1.f;      // 2^s applied to the weights when they are packed (fp16 planes stay normal)
   float acc_scale = 1.f;     // 2^-s, undone in the epilogue
@@ -37,13 +38,17 @@ struct UmmaExtra {
 
 // w_oihw may be null: the packed planes are then zero-filled and written later by umma_pack_device
 int umma_prepare_weights(UmmaConv& u, int precision, const float* w_oihw, int cout, int cin, int kh, int kw, int stride,
-                         int pad, int in_dtype, bool has_prologue, int out_nchw, bool in_interleaved, cudaStream_t st);
+                         int pad, int in_dtype, bool has_prologue, int out_nchw, bool in_interleaved, cudaStream_t st,
+                         bool rect_ok = false);
 // power-of-two weight pre-scale so that wmax lands in [2^(top-1), 2^top) (fp16x3 only)
 void umma_set_prescale(UmmaConv& u, float wmax, int top);
-// (re)pack the planes on the device from the fp32 [kh*kw*w_cin][cout_pad] matrix (k = tap*w_cin + c) of a w_cin -> w_cout convolution:
-// dgrad = false: `u` is that convolution; dgrad = true: `u` is its data-gradient convolution (w_cout -> w_cin, flipped filter).
+bool umma_disabled();                                             // YOLO_B200_DISABLE_UMMA
+// (re)pack the planes on the device from the fp32 [kh*kw*w_cin][cout_pad] matrix (k = tap*w_cin + c) of a w_cin -> w_cout convolution, in
+// one launch: `fwd` is that convolution (may be null / not eligible), `dg` its data-gradient convolution (n_dg = 1: w_cout -> w_cin with
+// a flipped filter) or the four parity classes py*2 + px of a 3x3 / stride 2 / pad 1 layer (n_dg = 4: dg[q].kh = 1 + py, .kw = 1 + px).
 // *sat_flag |= 2 when a scaled weight leaves the fp16 range.
-int umma_pack_device(const UmmaConv& u, const float* w_mat, int w_cin, int w_cout, int cout_pad, bool dgrad, int* sat_flag, cudaStream_t st);
+int umma_pack_device(const UmmaConv* fwd, const UmmaConv* dg, int n_dg, const float* w_mat, int w_cin, int w_cout, int cout_pad, int kh, int kw,
+                     int* sat_flag, cudaStream_t st);
 int umma_build_maps(UmmaConv& u, void* in_base, int max_batch, int H, int W, int C, int cpitch, int coff);
 int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, UmmaExtra* ex = nullptr);
 size_t umma_stats_groups(int M);

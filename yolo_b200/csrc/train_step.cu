@@ -100,6 +100,8 @@ struct TrainLayer {                       // per conv op
   __half* dz = nullptr;  long long dz_plane_rows = 0; // scaled pre-activation gradient [2][dz_plane_rows][Cout]
   __half* dzd = nullptr; long long dzd_plane_rows = 0; int dzd_n = 0;   // stride > 1: the same, zero-dilated to the input resolution
   UmmaConv dgrad;                                     // data-gradient convolution (Cout -> Cin, flipped filter)
+  UmmaConv dgrad_par[4];                              // 3x3 / stride 2 / pad 1: one dense convolution over dz per input-pixel parity class
+  bool dgrad_parity = false;
   WgradPlan wg;
   float* wT = nullptr; int cin_pad = 0;               // FFMA data gradient (head convs): flipped fp32 weights
   bool fwd_umma = false;
@@ -636,14 +638,25 @@ __global__ void wflip_kernel(const float* __restrict__ Wm, int kh, int kw, int C
   }
 }
 
-__global__ void adam_kernel(float* __restrict__ P, const float* __restrict__ G, float* __restrict__ M1, float* __restrict__ M2, size_t n,
-                            float lr_t, float rescale, float b1, float b2, float eps) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float g = G[i] * rescale;
-    const float m = b1 * M1[i] + (1.f - b1) * g;
-    const float v = b2 * M2[i] + (1.f - b2) * g * g;
-    M1[i] = m; M2[i] = v;
-    P[i] -= lr_t * m / (sqrtf(v) + eps);
+__device__ __forceinline__ void adam_one(float& p, float g, float& m1, float& m2, float lr_t, float rescale, float b1, float b2, float eps) {
+  g *= rescale;
+  const float m = b1 * m1 + (1.f - b1) * g;
+  const float v = b2 * m2 + (1.f - b2) * g * g;
+  m1 = m; m2 = v;
+  p -= lr_t * m / (sqrtf(v) + eps);
+}
+// 28 bytes of traffic per parameter: four floats per thread keep enough bytes in flight (n is a multiple of 4, the arrays 16-byte aligned)
+__global__ void __launch_bounds__(256)
+adam_kernel(float4* __restrict__ P, const float4* __restrict__ G, float4* __restrict__ M1, float4* __restrict__ M2, size_t n4,
+            float lr_t, float rescale, float b1, float b2, float eps) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 p = P[i], m1 = M1[i], m2 = M2[i];
+    const float4 g = G[i];
+    adam_one(p.x, g.x, m1.x, m2.x, lr_t, rescale, b1, b2, eps);
+    adam_one(p.y, g.y, m1.y, m2.y, lr_t, rescale, b1, b2, eps);
+    adam_one(p.z, g.z, m1.z, m2.z, lr_t, rescale, b1, b2, eps);
+    adam_one(p.w, g.w, m1.w, m2.w, lr_t, rescale, b1, b2, eps);
+    M1[i] = m1; M2[i] = m2; P[i] = p;
   }
 }
 
@@ -680,6 +693,7 @@ void train_release(yolo_handle* h, bool writeback) {
     TrainLayer& L = T->layers[i];
     const size_t K = (size_t)op.kh * op.kw * op.in.C;
     umma_release(L.dgrad);
+    for (UmmaConv& u : L.dgrad_par) umma_release(u);
     if (!writeback) { if (op.w_f32_own) op.w_f32 = op.w_f32_own; continue; }
     if (op.w_f32_own) {
       cudaMemcpy(op.w_f32_own, T->P + L.o_w, K * op.cout_pad * 4, cudaMemcpyDeviceToDevice);
@@ -766,9 +780,8 @@ static int repack_weights(yolo_handle* h, cudaStream_t st) {
   for (size_t i = 0; i < h->ops.size(); ++i) {
     Op& op = h->ops[i];
     TrainLayer& L = T->layers[i];
-    int rc = umma_pack_device(op.umma, T->P + L.o_w, op.in.C, op.cout, op.cout_pad, false, h->d_flags, st);
-    if (rc) return rc;
-    rc = umma_pack_device(L.dgrad, T->P + L.o_w, op.in.C, op.cout, op.cout_pad, true, h->d_flags, st);
+    int rc = umma_pack_device(&op.umma, L.dgrad_parity ? L.dgrad_par : &L.dgrad, L.dgrad_parity ? 4 : 1, T->P + L.o_w, op.in.C, op.cout, op.cout_pad,
+                              op.kh, op.kw, h->d_flags, st);
     if (rc) return rc;
     if (L.wT) {
       wflip_kernel<<<grid_for((size_t)op.kh * op.kw * op.in.C * op.cout), 256, 0, st>>>(T->P + L.o_w, op.kh, op.kw, op.in.C, op.cout, op.cout_pad, L.wT, L.cin_pad);
@@ -785,6 +798,9 @@ extern "C" int yolo_train_init(yolo_handle* h, float* params_flat, float* grads_
   if (h->spec.precision != YOLO_PREC_FP16X3) return hfail(h, fail(YOLO_E_UNSUPPORTED, "train_init: training runs in YOLO_PREC_FP16X3 (fp32-grade on the tensor cores)"));
   if (h->spec.net_type != YOLO_NET_CARNET && h->spec.net_type != YOLO_NET_CARLPNET) return hfail(h, fail(YOLO_E_UNSUPPORTED, "train_init: CARNET / CARLPNET only"));
   if (n_flat != yolo_train_flat_size(h)) return hfail(h, fail(YOLO_E_SHAPE, "train_init: flat buffers must hold %zu floats", yolo_train_flat_size(h)));
+  if ((reinterpret_cast<uintptr_t>(params_flat) | reinterpret_cast<uintptr_t>(grads_flat) | reinterpret_cast<uintptr_t>(adam_m) |
+       reinterpret_cast<uintptr_t>(adam_v)) & 15)
+    return hfail(h, fail(YOLO_E_BADARG, "train_init: the flat buffers must be 16-byte aligned"));
   for (const Op& op : h->ops)
     if (op.kind != OP_CONV || op.p_prebn >= 0 || op.out_nchw || (op.p_bn >= 0 && op.cout % 8)) return hfail(h, fail(YOLO_E_UNSUPPORTED, "train_init: unsupported op in the plan"));
   YB_CUDA(cudaSetDevice(h->device));
@@ -829,7 +845,14 @@ extern "C" int yolo_train_init(yolo_handle* h, float* params_flat, float* grads_
       L.dz_plane_rows = (long long)(B + g) * L.Ho * L.Wo;
       tmp[i].dz = take((size_t)2 * L.dz_plane_rows * op.cout * 2);
       tmp[i].dzd = (size_t)-1;
-      if (op.stride > 1 && op.in.buf >= 0) {
+      // 3x3 / stride 2 / pad 1 (every Darknet down-sampling conv): four parity-class convolutions over dz instead of one convolution
+      // over a zero-dilated copy - a quarter of the MMAs and no dilated buffer (YOLO_B200_DGRAD_PARITY=0 keeps the dilated path)
+      {
+        const char* e = getenv("YOLO_B200_DGRAD_PARITY");
+        L.dgrad_parity = op.stride == 2 && op.kh == 3 && op.kw == 3 && op.pad == 1 && op.in.buf >= 0 && op.in.H % 2 == 0 && op.in.W % 2 == 0 &&
+                         op.cout % 32 == 0 && !umma_disabled() && !(e && e[0] == '0');
+      }
+      if (op.stride > 1 && op.in.buf >= 0 && !L.dgrad_parity) {
         const int gd = (kGuardRows + op.in.H * op.in.W - 1) / (op.in.H * op.in.W);
         L.dzd_n = B + gd;
         L.dzd_plane_rows = (long long)L.dzd_n * op.in.H * op.in.W;
@@ -934,8 +957,23 @@ extern "C" int yolo_train_init(yolo_handle* h, float* params_flat, float* grads_
     if (L.has_bn && op.in.buf >= 0) {
       // data-gradient convolution over dz (or its zero-dilated copy): Cout -> Cin, stride 1, pad k-1-p, flipped filter
       const bool dil = op.stride > 1;
+      if (L.dgrad_parity) {
+        const int nimg = (int)(L.dz_plane_rows / ((long long)L.Ho * L.Wo));
+        for (int q = 0; q < 4; ++q) {
+          UmmaConv& u = L.dgrad_par[q];
+          rc = umma_prepare_weights(u, YOLO_PREC_FP16X3, nullptr, cin, cout, 1 + (q >> 1), 1 + (q & 1), 1, 0, DT_F16X2, false, 0, false, st, true);
+          if (rc) return hfail(h, rc);
+          if (!u.eligible) return hfail(h, fail(YOLO_E_UNSUPPORTED, "train_init: parity data gradient of layer %s is not a tensor-core shape", op.name.c_str()));
+          umma_set_prescale(u, wmax, 5);
+          u.pad_high_full = true;
+          rc = umma_build_maps(u, L.dz, nimg, L.Ho, L.Wo, cout, cout, 0);
+          if (rc) return hfail(h, rc);
+          if (!u.enabled) return hfail(h, fail(YOLO_E_UNSUPPORTED, "train_init: no tensor map for the parity data gradient of layer %s", op.name.c_str()));
+        }
+      } else {
       rc = umma_prepare_weights(L.dgrad, YOLO_PREC_FP16X3, nullptr, cin, cout, op.kh, op.kw, 1, op.kh - 1 - op.pad, DT_F16X2, false, 0, false, st);
       if (rc) return hfail(h, rc);
+      }
       if (L.dgrad.eligible) {
         umma_set_prescale(L.dgrad, wmax, 5);
         const int Hd = dil ? op.in.H : L.Ho, Wd = dil ? op.in.W : L.Wo;
@@ -943,7 +981,7 @@ extern "C" int yolo_train_init(yolo_handle* h, float* params_flat, float* grads_
         rc = umma_build_maps(L.dgrad, dil ? (void*)L.dzd : (void*)L.dz, nimg, Hd, Wd, cout, cout, 0);
         if (rc) return hfail(h, rc);
       }
-      if (!L.dgrad.enabled) {                                      // FFMA data gradient on flipped fp32 weights
+      if (!L.dgrad.enabled && !L.dgrad_parity) {                   // FFMA data gradient on flipped fp32 weights
         if (tmp[i].wT == (size_t)-1) return hfail(h, fail(YOLO_E_UNSUPPORTED, "train_init: no data-gradient kernel for layer %s", op.name.c_str()));
         L.wT = reinterpret_cast<float*>(T->arena + tmp[i].wT);
       }
@@ -1193,7 +1231,16 @@ static int train_fwd_bwd(yolo_handle* h, const void* input, int in_layout, const
         d.act = ACT_NONE;
         d.out = grad_ptr(h, op.in); d.out_dtype = DT_F32; d.Ho = op.in.H; d.Wo = op.in.W; d.out_cpitch = grad_pitch(op.in); d.out_coff = op.in.coff;
         d.sat_flag = h->d_flags;
-        if (L.dgrad.enabled) {
+        if (L.dgrad_parity) {
+          d.in = L.dz; d.H = L.Ho; d.W = L.Wo; d.in_plane_stride = L.dz_plane_rows * C; d.pad = 0; d.Ho = L.Ho; d.Wo = L.Wo;
+          for (int q = 0; q < 4 && !rc; ++q) {
+            d.kh = 1 + (q >> 1); d.kw = 1 + (q & 1);
+            d.upsample2 = 2 + q;                                      // epilogue: pixel (2a + py, 2b + px) of the input gradient
+            UmmaExtra ex;
+            ex.acc_scale_dev = L.dzscale + 1; ex.accum = L.dgrad_accum ? 1 : 0;
+            rc = launch_conv_umma(L.dgrad_par[q], d, st, &ex);
+          }
+        } else if (L.dgrad.enabled) {
           UmmaExtra ex;
           ex.acc_scale_dev = L.dzscale + 1; ex.accum = L.dgrad_accum ? 1 : 0;
           rc = launch_conv_umma(L.dgrad, d, st, &ex);
@@ -1280,7 +1327,9 @@ extern "C" int yolo_train_apply(yolo_handle* h, float lr, float beta1, float bet
   const int launches0 = g_launches;
   const int t = ++T->step_count;
   const float lr_t = lr * sqrtf(1.f - powf(beta2, (float)t)) / (1.f - powf(beta1, (float)t));     // mxnet.optimizer.Adam
-  adam_kernel<<<grid_for(T->n_flat), 256, 0, st>>>(T->P, T->G, T->M1, T->M2, T->n_flat, lr_t, rescale_grad, beta1, beta2, eps);
+  adam_kernel<<<grid_for(T->n_flat / 4, 256, 148 * 16), 256, 0, st>>>(reinterpret_cast<float4*>(T->P), reinterpret_cast<const float4*>(T->G),
+                                                                      reinterpret_cast<float4*>(T->M1), reinterpret_cast<float4*>(T->M2), T->n_flat / 4, lr_t,
+                                                                      rescale_grad, beta1, beta2, eps);
   ++g_launches;
   int rc = repack_weights(h, st);                                 // fp16 planes of both convolution directions follow the master weights
   if (rc) return hfail(h, rc);
