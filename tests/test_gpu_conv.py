@@ -79,3 +79,43 @@ def test_single_layer(shape, precision, tol):
     err = np.abs(out - ref)
     scale = max(1.0, float(np.abs(ref).max()))
     assert err.max() <= tol * scale, f"{precision} {shape}: max err {err.max():.3e} (scale {scale:.2f}), mean {err.mean():.3e}"
+
+
+# The 3-channel stem (FFMA kernels: 16 x 32-pixel tiles with the input patch staged in shared memory and packed fma.f32x2 for
+# Cout 16 / 32; the pixel-per-thread kernel otherwise), reached through the harness's "pre" layer, on both input contracts of
+# the reference (NCHW fp32 in [0,1], cv_img_2_ndarray; uint8 HWC camera frames with the /255 fused) and on ragged tiles.
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-6), ("fp16x3", 2e-6), ("bf16x6", 2e-6)])
+@pytest.mark.parametrize("u8", [False, True])
+@pytest.mark.parametrize("B,H,W,cout", [(2, 32, 64, 32), (3, 23, 45, 32), (2, 17, 33, 16), (1, 40, 24, 8), (2, 16, 32, 64)])
+def test_stem(B, H, W, cout, u8, precision, tol):
+    import yolo_b200
+    rng = np.random.default_rng(B * 1000 + H)
+    spec = dict(size=[H, W], cin=cout, cout=8, k=1, stride=1, pad=0, act=0, residual=0, bn=0)
+    net = yolo_b200.Net("debugconv", spec, precision=precision, max_batch=B)
+    params = {}
+    for name, shape in net.param_shapes():
+        leaf = name.rsplit(".", 1)[1]
+        if leaf == "weight":
+            params[name] = (rng.standard_normal(shape) / np.sqrt(shape[1] * shape[2] * shape[3])).astype(np.float32)
+        elif leaf in ("gamma", "running_var"):
+            params[name] = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+        else:
+            params[name] = rng.normal(0, 0.3, shape).astype(np.float32)
+    net.load_params(params)
+    if u8:
+        frames = rng.integers(0, 256, size=(B, H, W, 3), dtype=np.uint8)
+        net.forward(data=torch.from_numpy(frames).cuda())
+        x = (torch.from_numpy(frames).permute(0, 3, 1, 2).float() / 255.0).double()      # the reference divides in fp32
+    else:
+        xf = rng.uniform(0, 1, size=(B, 3, H, W)).astype(np.float32)
+        net.forward(data=torch.from_numpy(xf).cuda())
+        x = torch.from_numpy(xf).double()
+    got = net.activation("pre", (B, cout, H, W))
+    y = F.conv2d(x, torch.from_numpy(params["pre.weight"]).double(), None, 1, 1)
+    g, b, m, v = (torch.from_numpy(params["pre." + n]).double() for n in ("gamma", "beta", "running_mean", "running_var"))
+    y = (y - m[None, :, None, None]) / torch.sqrt(v[None, :, None, None] + 1e-5) * g[None, :, None, None] + b[None, :, None, None]
+    ref = F.leaky_relu(y, 0.1).numpy()
+    scale = max(1.0, float(np.abs(ref).max()))
+    err = np.abs(got - ref).max()
+    assert err <= tol * scale, f"stem {precision} u8={u8} {(B, H, W, cout)}: max err {err:.3e} (scale {scale:.2f})"
+    assert net.saturated() == 0

@@ -50,6 +50,7 @@ struct ConvDesc {
   int in_dil;                  // >1: the input is implicitly zero-dilated (data-gradient of a strided conv); 0/1 = off
   const float* w_f32;          // [kh*kw*Cin][CoutPad4] fp32 (SIMT path), k = (r*kw+s)*Cin + c
   int cout_pad;                // row pitch of w_f32
+  const float* w_host;         // host copy of w_f32 when it is static (inference stem: weights travel as kernel parameters), else null
   // prologue on the input (DenseNet pre-activation BN->ReLU): v = relu(v*pre_scale[c] + pre_shift[c])
   const float* pre_scale;  const float* pre_shift;
   // epilogue: y = act(acc*scale[o] + shift[o]) (+ residual)

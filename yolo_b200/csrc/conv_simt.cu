@@ -513,6 +513,168 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const __grid_constant__ Co
   }
 }
 
+// ---- stem, tiled: 16 x 16*PX output pixels per block, input patch staged in shared memory, packed FFMA2 --------------------
+// The pixel-per-thread kernel above gathers its 27 taps from global memory (27 byte loads + 27 IEEE divisions per pixel for camera
+// frames) and issues one FFMA per multiply-add.  Here the block converts its (16+2) x (32+2) x 3 input patch ONCE into shared
+// memory (coalesced row segments; /255 once per input element), each thread owns PX pixels (columns tx + 16p of one tile row)
+// x all CO output channels, and the multiply-adds are `fma.rn.f32x2` on (channel pair) registers - two IEEE fp32 FMAs per issue
+// slot, bit-identical to scalar fmaf in the same k order.  Results leave through the same swizzled staging as above.
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long dup2(float x) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(x));
+  return d;
+}
+// WCONST: the weights travel as a kernel parameter (3.4 KB in constant bank 0).  With every index unrolled the compiler feeds them to
+// FFMA2 through uniform registers (LDCU.128), so the shared-memory pipe - saturated at 95 % by the broadcast weight loads of the
+// shared-memory variant (profiles/r2_ncu_stem.txt) - only carries the input patch and the staged results.  Training reads the master
+// weights from the flat device buffer and keeps the shared-memory variant.
+constexpr int STEM_TH = 16;
+struct StemWeights { float w[27 * 32]; };
+template <class FO, int LAYOUT, int CO, int PX, bool WCONST>
+__global__ void __launch_bounds__(256, PX == 2 ? 2 : 4) stem3x3_tile_kernel(const __grid_constant__ ConvKArgs args, const __grid_constant__ StemWeights wp) {
+  using TOut = typename FO::T;
+  constexpr int TW = 16 * PX, IW = (TW + 2) * 3;
+  constexpr int IPITCH = PX == 2 ? 112 : 80;                       // >= IW and = 16 mod 32: the two tile rows of a warp hit disjoint banks
+  const ConvDesc& d = args.d;
+  extern __shared__ __align__(16) float s_w[];                     // [27][CO], scale[CO], shift[CO], patch[18][IPITCH], staged out
+  float* s_sc = s_w + 27 * CO;
+  float* s_sh = s_sc + CO;
+  float* s_in = s_sh + CO;
+  TOut* s_out = reinterpret_cast<TOut*>(s_in + (STEM_TH + 2) * IPITCH);               // [NP][256*PX][CO]
+  const int tid = threadIdx.x;
+  const int tiles_w = (d.Wo + TW - 1) / TW, tiles_h = (d.Ho + STEM_TH - 1) / STEM_TH;
+  const int tw = blockIdx.x % tiles_w, th = (blockIdx.x / tiles_w) % tiles_h, n = blockIdx.x / (tiles_w * tiles_h);
+  const int oh0 = th * STEM_TH, ow0 = tw * TW;
+  if (!WCONST)
+    for (int i = tid; i < 27 * CO; i += 256) s_w[i] = __ldg(d.w_f32 + i);
+  for (int i = tid; i < CO; i += 256) {
+    s_sc[i] = d.scale ? __ldg(d.scale + i) : 1.f;
+    s_sh[i] = d.shift ? __ldg(d.shift + i) : 0.f;
+  }
+  for (int i = tid; i < (STEM_TH + 2) * IW; i += 256) {
+    const int row = i / IW, rem = i - row * IW;
+    const int ih = oh0 - 1 + row;
+    int col, c;
+    if (LAYOUT == IN_NCHW_F32) { c = rem / (TW + 2); col = rem - c * (TW + 2); }                // column fastest: coalesced per channel plane
+    else { col = rem / 3; c = rem - col * 3; }                                                  // byte order of the camera frame
+    const int iw = ow0 - 1 + col;
+    float v = 0.f;
+    if ((unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W) {
+      if (LAYOUT == IN_NCHW_F32) v = __ldg(static_cast<const float*>(d.in) + ((size_t)(n * 3 + c) * d.H + ih) * d.W + iw);
+      else v = (float)__ldg(static_cast<const unsigned char*>(d.in) + ((size_t)(n * d.H + ih) * d.W + iw) * 3 + c) / 255.f;
+    }
+    s_in[row * IPITCH + col * 3 + c] = v;
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  unsigned long long acc[PX][CO / 2];
+#pragma unroll
+  for (int p = 0; p < PX; ++p)
+#pragma unroll
+    for (int j = 0; j < CO / 2; ++j) acc[p][j] = 0ull;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float* row = s_in + (ty + r) * IPITCH + tx * 3;
+#pragma unroll
+    for (int qc = 0; qc < 9; ++qc) {                                // (q, c) in the order of the weight rows: k = (r*3 + q)*3 + c
+      unsigned long long x[PX];
+#pragma unroll
+      for (int p = 0; p < PX; ++p) x[p] = dup2(row[p * 16 * 3 + qc]);
+      const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(s_w + (r * 9 + qc) * CO);
+      const unsigned long long* wc = reinterpret_cast<const unsigned long long*>(wp.w) + (r * 9 + qc) * (CO / 2);
+#pragma unroll
+      for (int j = 0; j < CO / 4; ++j) {
+        ulonglong2 w;
+        if constexpr (WCONST) { w.x = wc[2 * j]; w.y = wc[2 * j + 1]; }
+        else w = w2[j];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          acc[p][2 * j] = ffma2(x[p], w.x, acc[p][2 * j]);
+          acc[p][2 * j + 1] = ffma2(x[p], w.y, acc[p][2 * j + 1]);
+        }
+      }
+    }
+  }
+  constexpr int BLK_PIX = STEM_TH * TW;
+  constexpr int SW_E = 16 / (int)sizeof(TOut);
+  constexpr int SW_VPP = CO / SW_E;
+  constexpr int SW_RPL = (128 / (CO * (int)sizeof(TOut))) > 0 ? (128 / (CO * (int)sizeof(TOut))) : 1;
+  int sat = 0;
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    const int pl = ty * TW + tx + 16 * p;
+    const int sw_x = (pl / SW_RPL) & (SW_VPP - 1);
+#pragma unroll
+    for (int j4 = 0; j4 < CO; j4 += 4) {
+      const float2 a = *reinterpret_cast<const float2*>(&acc[p][j4 / 2]), b = *reinterpret_cast<const float2*>(&acc[p][j4 / 2 + 1]);
+      const float raw[4] = {a.x, a.y, b.x, b.y};
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y = fmaf(raw[j], s_sc[j4 + j], s_sh[j4 + j]);
+        if (d.act == ACT_LEAKY) y = y > 0.f ? y : 0.1f * y;
+        else if (d.act == ACT_RELU) y = fmaxf(y, 0.f);
+        v[j] = y;
+      }
+      const int vi = j4 / SW_E, within = j4 - vi * SW_E;
+      store4f<FO>(s_out + (size_t)pl * CO + ((vi ^ sw_x) * SW_E) + within, (long long)BLK_PIX * CO, v, sat);
+    }
+  }
+  // (pixels of a ragged tile outside the image are computed on zero padding and never stored; they cannot overflow the format either)
+  if (sat && d.sat_flag) atomicOr(d.sat_flag, YOLO_SAT_ACT_FFMA);
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < FO::NP; ++q) {
+    const uint4* src = reinterpret_cast<const uint4*>(s_out + (size_t)q * BLK_PIX * CO);
+    TOut* dst = static_cast<TOut*>(d.out) + (size_t)q * d.out_plane_stride + d.out_coff;
+    for (int i = tid; i < BLK_PIX * SW_VPP; i += 256) {
+      const int pix = i / SW_VPP, vi = i - pix * SW_VPP;
+      const int oh = oh0 + pix / TW, ow = ow0 + pix % TW;
+      if (oh < d.Ho && ow < d.Wo)
+        *reinterpret_cast<uint4*>(dst + ((size_t)(n * d.Ho + oh) * d.Wo + ow) * d.out_cpitch + vi * SW_E) =
+            src[pix * SW_VPP + (vi ^ ((pix / SW_RPL) & (SW_VPP - 1)))];
+    }
+  }
+}
+
+template <class FO, int CO, int PX>
+static int launch_stem_tile_t(const ConvKArgs& a, int in_layout, cudaStream_t st) {
+  const ConvDesc& d = a.d;
+  constexpr int TW = 16 * PX, IPITCH = PX == 2 ? 112 : 80;
+  const int smem = (27 * CO + 2 * CO + (STEM_TH + 2) * IPITCH) * 4 + FO::NP * STEM_TH * TW * CO * (int)sizeof(typename FO::T);
+  const int blocks = d.N * ((d.Ho + STEM_TH - 1) / STEM_TH) * ((d.Wo + TW - 1) / TW);
+  StemWeights wp;
+  static const bool const_off = [] { const char* e = getenv("YOLO_B200_STEM_WCONST"); return e && e[0] == '0'; }();
+  if (d.w_host && !const_off) {                                 // [27][CO] rows (cout_pad == Cout is part of stem_eligible)
+    memcpy(wp.w, d.w_host, sizeof(float) * 27 * CO);
+    int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_tile_kernel<FO, IN_NCHW_F32, CO, PX, true>), 160 * 1024);
+    if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_tile_kernel<FO, IN_NHWC_U8, CO, PX, true>), 160 * 1024);
+    if (rc) return rc;
+    if (in_layout == IN_NCHW_F32) stem3x3_tile_kernel<FO, IN_NCHW_F32, CO, PX, true><<<blocks, 256, smem, st>>>(a, wp);
+    else stem3x3_tile_kernel<FO, IN_NHWC_U8, CO, PX, true><<<blocks, 256, smem, st>>>(a, wp);
+    return YOLO_OK;
+  }
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_tile_kernel<FO, IN_NCHW_F32, CO, PX, false>), 160 * 1024);
+  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_tile_kernel<FO, IN_NHWC_U8, CO, PX, false>), 160 * 1024);
+  if (rc) return rc;
+  if (in_layout == IN_NCHW_F32) stem3x3_tile_kernel<FO, IN_NCHW_F32, CO, PX, false><<<blocks, 256, smem, st>>>(a, wp);
+  else stem3x3_tile_kernel<FO, IN_NHWC_U8, CO, PX, false><<<blocks, 256, smem, st>>>(a, wp);
+  return YOLO_OK;
+}
+template <class FO>
+static int launch_stem_tile(const ConvKArgs& a, int in_layout, cudaStream_t st) {
+  // one pixel per thread: 64 registers and 40 KB per block -> four blocks per SM hide the load and store phases of each other
+  // (two pixels per thread reuse every weight load twice but fit one or two blocks: YOLO_B200_STEM_PX=2, measured slower)
+  static const bool px2 = [] { const char* e = getenv("YOLO_B200_STEM_PX"); return e && e[0] == '2'; }();
+  if (px2) return a.d.Cout == 32 ? launch_stem_tile_t<FO, 32, 2>(a, in_layout, st) : launch_stem_tile_t<FO, 16, 2>(a, in_layout, st);
+  return a.d.Cout == 32 ? launch_stem_tile_t<FO, 32, 1>(a, in_layout, st) : launch_stem_tile_t<FO, 16, 1>(a, in_layout, st);
+}
+
 template <class FO, int PX>
 static int launch_stem_t(const ConvKArgs& a, int in_layout, int smem, cudaStream_t st) {
   const int blocks = (a.M + 256 * PX - 1) / (256 * PX);
@@ -541,6 +703,23 @@ int launch_stem(const ConvDesc& d, int in_layout, cudaStream_t st) {
   auto smem_for = [&](int px) { return (27 * d.cout_pad + 2 * d.Cout) * 4 + npl * 256 * px * d.Cout * esz; };   // weights, scale/shift, staged rows
   const bool two = smem_for(2) <= 150 * 1024;                 // two pixels per thread whenever the staged rows fit
   int rc;
+  static const bool tile_off = [] { const char* e = getenv("YOLO_B200_STEM_TILE"); return e && e[0] == '0'; }();
+  const size_t osz = (size_t)esz;
+  const bool tiled = !tile_off && d.stride == 1 && d.pad == 1 && d.Ho == d.H && d.Wo == d.W && (d.Cout == 16 || d.Cout == 32) &&
+                     (d.Cout * osz) % 16 == 0 && (d.out_cpitch * osz) % 16 == 0 && (d.out_coff * osz) % 16 == 0 &&
+                     ((size_t)d.out_plane_stride * osz) % 16 == 0 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0;
+  if (tiled) {
+    switch (d.out_dtype) {
+      case DT_F32: rc = launch_stem_tile<FmtF32>(a, in_layout, st); break;
+      case DT_BF16: rc = launch_stem_tile<FmtBF16>(a, in_layout, st); break;
+      case DT_BF16X3: rc = launch_stem_tile<FmtBF16X3>(a, in_layout, st); break;
+      default: rc = launch_stem_tile<FmtF16X2>(a, in_layout, st); break;
+    }
+    if (rc) return rc;
+    ++g_launches;
+    YB_CUDA(cudaGetLastError());
+    return YOLO_OK;
+  }
   switch (d.out_dtype) {
     case DT_F32: rc = two ? launch_stem_t<FmtF32, 2>(a, in_layout, smem_for(2), st) : launch_stem_t<FmtF32, 1>(a, in_layout, smem_for(1), st); break;
     case DT_BF16: rc = two ? launch_stem_t<FmtBF16, 2>(a, in_layout, smem_for(2), st) : launch_stem_t<FmtBF16, 1>(a, in_layout, smem_for(1), st); break;

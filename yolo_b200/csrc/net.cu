@@ -382,6 +382,7 @@ void fill_conv_desc(const yolo_handle* h, const Op& op, int batch, const void* i
   d.in_cpitch = op.in.cpitch; d.in_coff = op.in.coff; d.in_plane_stride = op.in.ps;
   d.kh = op.kh; d.kw = op.kw; d.stride = op.stride; d.pad = op.pad; d.Cout = op.cout;
   d.w_f32 = op.w_f32; d.cout_pad = op.cout_pad;
+  d.w_host = (op.w_f32 == op.w_f32_own && !op.w_stem_host.empty()) ? op.w_stem_host.data() : nullptr;     // stale while a trainer owns the weights
   d.pre_scale = op.pre_scale; d.pre_shift = op.pre_shift;
   d.scale = op.scale; d.shift = op.shift; d.act = op.act;
   if (op.has_res) { d.res = resolve(h, op.res, input, outputs); d.res_cpitch = op.res.cpitch; d.res_coff = op.res.coff; d.res_plane_stride = op.res.ps; }
@@ -539,6 +540,8 @@ extern "C" int yolo_finalize_params(yolo_handle* h, void* stream) {
           for (int s2 = 0; s2 < kw; ++s2)
             wd[((size_t)(r * kw + s2) * cin + c) * op.cout_pad + o] = W[(((size_t)o * creal + c) * kh + r) * kw + s2];
     op.w_f32 = op.w_f32_own = reinterpret_cast<float*>(dbase + slots[i].w);
+    op.w_stem_host.clear();
+    if (cin == 3 && kh == 3 && kw == 3 && cout <= 32 && op.cout_pad == cout) op.w_stem_host.assign(wd, wd + (size_t)27 * op.cout_pad);
     std::vector<float> sc, sh;
     op.scale = op.shift = op.pre_scale = op.pre_shift = nullptr;
     if (op.p_bn >= 0) {

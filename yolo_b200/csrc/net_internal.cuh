@@ -49,6 +49,7 @@ struct Op {
   int p_weight = -1, p_bias = -1, p_bn = -1, p_prebn = -1;   // index of the FIRST param of each group
   // device parameter pointers (valid after finalize)
   float* w_f32 = nullptr;
+  std::vector<float> w_stem_host;   // 3-channel 3x3 stem: host copy of the [27][cout_pad] matrix (kernel-parameter weights)
   float* w_f32_own = nullptr;  // the handle's own copy in the parameter arena (w_f32 points into the trainer's flat buffer while training)
   int cout_pad = 0;
   float *scale = nullptr, *shift = nullptr, *pre_scale = nullptr, *pre_shift = nullptr;

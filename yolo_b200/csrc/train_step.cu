@@ -701,6 +701,7 @@ void train_release(yolo_handle* h, bool writeback) {
     }
     std::vector<float> tmp(K * op.cout_pad);
     if (cudaMemcpy(tmp.data(), T->P + L.o_w, tmp.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      if (!op.w_stem_host.empty() && op.w_stem_host.size() == tmp.size()) op.w_stem_host = tmp;      // kernel-parameter copy of the stem
       std::vector<float>& Wh = h->params[op.p_weight].host;
       for (int o = 0; o < op.cout; ++o)
         for (int c = 0; c < op.in.C; ++c)
