@@ -92,6 +92,7 @@ struct UmmaParams {
 //
 // Warps: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = accumulation/epilogue group 0, 6..9 = group 1.
 constexpr int GROUP_THREADS = 128;
+constexpr int STAGE_OUT_BYTES = 32 * 64;   // store-transpose buffer of one epilogue warp
 
 // Column sums over the 32 lanes of a warp of 32 values per lane, transposing butterfly: 31 shuffles instead of 160;
 // lane l returns the sum of v[l] over all lanes.  `v` is clobbered.
@@ -151,6 +152,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t bar_cfull = bar_pfull + 32, bar_cempty = bar_pfull + 48;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 16 * MAX_STAGES + 64);
   float* s_scale_all = reinterpret_cast<float*>(aux + 16 * MAX_STAGES + 128);      // [group][2][BN]: scale, shift
+  // per epilogue warp: 32 rows x 64 bytes (one 32-channel chunk of one plane), 64-byte-swizzled - the transpose buffer of the stores
+  unsigned char* s_stage_all = aux + ((16 * MAX_STAGES + 128 + 2 * 2 * p.BN * 4 + 127) & ~127);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
@@ -388,7 +391,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       for (int i = et; i < gcols; i += GROUP_THREADS) {
         const int n = n0 + i;
-        s_scale[i] = (p.scale && n < p.Cout) ? __ldg(p.scale + n) : 1.f;
+        // the accumulator scale is a power of two (weight pre-scale, dynamic gradient scale): folding it into the BN scale is exact
+        s_scale[i] = ((p.scale && n < p.Cout) ? __ldg(p.scale + n) : 1.f) * acc_scale;
         s_scale[gcols + i] = (p.shift && n < p.Cout) ? __ldg(p.shift + n) : 0.f;
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
@@ -444,38 +448,58 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (!WIDE) asm volatile("bar.arrive %0, 256;" ::"r"(4 - group) : "memory");         // the other group's turn
 
       // ---- epilogue from registers: BN affine, activation, residual, format split, store ----
-      // (kept compact on purpose: the first version of this block was 17k SASS instructions and stalled on
-      //  instruction fetch - profiles/r1_ncu_summary.md)
+      // ONE copy of the 32-column code, executed nchunks times on acc[0] with the other chunks rotated down through registers.
+      // Unrolled over the four chunks it was 4500 straight-line SASS instructions per tile and spent half of its time waiting
+      // for instruction fetch (ncu: stall_no_inst 48 % of the epilogue samples, ~15 us per tile - exposed on the wide kinds,
+      // where both groups work on the same tile, and the whole cost of the short-K 1x1 layers; profiles/r2_ncu_conv_1x1.txt).
       const int m = m0 + row;
       const bool valid = m < p.M && p.dbg_nostore != 2;
-      if (!valid && !STATS) continue;                      // with statistics the whole warp takes part in the shuffles
-      size_t pix[4];
-      int npix = 1;
-      if (p.upsample2) {
+      // 16-bit outputs leave through a per-warp transpose: a thread owns one pixel row (64 contiguous bytes per plane and chunk), so
+      // a direct STG.128 touches 32 different lines per instruction and the LSU pays 32 tag cycles for 512 bytes (measured: the
+      // stores were 70 % of the epilogue, 6.7 us per 256 x 256 tile).  Staged through shared memory, lane l stores 16 bytes of row
+      // (l >> 2) + 8 i: 8 lines per instruction, whole 32-byte sectors.  Rows are addressed by their pixel index, computed here
+      // once per tile for the four rows a lane stores.
+      bool rvalid[4];
+      int rpix[4];
+      if (!OUT_F32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int mr = m0 + lane_grp * 32 + (lane >> 2) + 8 * i;
+          rvalid[i] = mr < p.M && p.dbg_nostore == 0;
+          if (p.upsample2) {
+            const int img = mr / HoWo, rem = mr - img * HoWo;
+            const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+            const int q = p.upsample2 == 1 ? 0 : p.upsample2 - 2;
+            rpix[i] = (img * 2 * p.Ho + 2 * oh + (q >> 1)) * (2 * p.Wo) + 2 * ow + (q & 1);
+          } else {
+            rpix[i] = mr;
+          }
+        }
+      }
+      unsigned char* s_stage = s_stage_all + (warp - 2) * STAGE_OUT_BYTES;
+      size_t pix0 = (size_t)m;                              // fp32 outputs: this thread's own row
+      if (OUT_F32 && p.upsample2 > 1) {
         const int img = m / HoWo, rem = m - img * HoWo;
         const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
-        if (p.upsample2 == 1) {                             // nearest 2x upsampling: four copies
-          npix = 4;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) pix[q] = ((size_t)img * 2 * p.Ho + 2 * oh + (q >> 1)) * (2 * p.Wo) + 2 * ow + (q & 1);
-        } else {                                            // 2 + parity class: one pixel of the 2x grid (strided data gradient)
-          const int q = p.upsample2 - 2;
-          pix[0] = ((size_t)img * 2 * p.Ho + 2 * oh + (q >> 1)) * (2 * p.Wo) + 2 * ow + (q & 1);
-        }
-      } else {
-        pix[0] = (size_t)m;
+        const int q = p.upsample2 - 2;
+        pix0 = ((size_t)img * 2 * p.Ho + 2 * oh + (q >> 1)) * (2 * p.Wo) + 2 * ow + (q & 1);
       }
+      const bool leaky = p.act == ACT_LEAKY, relu = p.act == ACT_RELU;
+      float ymax = 0.f;                                     // max |value| this thread stores into a high plane (saturation flag)
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        if (c > 0) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+          for (int i = 0; i < 32; ++i) { acc[0][i] = acc[1][i]; acc[1][i] = acc[2][i]; acc[2][i] = acc[3][i]; }
+        }
         const int c0 = c * 32;
         const int nb = n0 + c0;
-        if (c >= nchunks || nb >= p.Cout) continue;
-        float* y = acc[c];
+        if (nb >= p.Cout) break;
+        float* y = acc[0];
         const int nvalid = min(32, p.Cout - nb);
         {
           const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
           const float4* sh4 = reinterpret_cast<const float4*>(s_scale + gcols + c0);
-          const bool leaky = p.act == ACT_LEAKY, relu = p.act == ACT_RELU;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 a = sc4[q], b = sh4[q];
@@ -487,7 +511,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               // profiles/r1_umma_precision.txt) that the next layer's K-sum amplifies.  Every partial carries the same expected
               // relative loss, so it is added back once, here (round-to-nearest of y*(1+c) is unbiased even for c < 1 ulp):
               // Darknet-53 head error vs fp64 2.7e-4 -> 0.9e-4 (profiles/r2_biascomp.txt).
-              float t = fmaf(fmaf(y[4 * q + e], p.bias_comp, y[4 * q + e]) * acc_scale, sc[e], sh[e]);
+              float t = fmaf(fmaf(y[4 * q + e], p.bias_comp, y[4 * q + e]), sc[e], sh[e]);
               t = leaky ? fmaxf(t, 0.1f * t) : (relu ? fmaxf(t, 0.f) : t);
               y[4 * q + e] = t;
             }
@@ -508,11 +532,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             sp[0] = s1;
             sp[p.Cout] = s2;
           }
-          if (!valid) continue;
         }
         if (OUT_F32) {                                      // head convs: fp32 NHWC == (B, H*W, A, C); gradient buffers (accum)
-          float* op = static_cast<float*>(p.out) + pix[0] * p.out_cpitch + p.out_coff + nb;
-          if (((p.out_cpitch | p.out_coff) & 3) == 0 && nvalid == 32) {
+          float* op = static_cast<float*>(p.out) + pix0 * p.out_cpitch + p.out_coff + nb;
+          if (!valid) {
+            // rows past the last pixel: nothing to store
+          } else if (((p.out_cpitch | p.out_coff) & 3) == 0 && nvalid == 32) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               float4 v = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
@@ -535,7 +560,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         } else {
           constexpr bool F16 = MODE == 2;
-          if (p.res) {                                      // residual add (DarknetBasicBlockV3), stored in the activation format
+          if (p.res && valid) {                             // residual add (DarknetBasicBlockV3), stored in the activation format
             const unsigned short* rp = static_cast<const unsigned short*>(p.res) + (size_t)m * p.res_cpitch + p.res_coff + nb;
 #pragma unroll
             for (int pl = 0; pl < NP; ++pl) {
@@ -564,16 +589,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               if (F16) {
-                float a = y[i], b = y[i + 1];
+                // the high plane saturates at the fp16 range (cvt.satfinite == clamp to +-65504): flagged below, never silent
+                // (yolo_check_saturation).  Columns >= nvalid hold stale TMEM and are never stored - nor tracked.
+                if (pl == 0 && i < nvalid && valid) ymax = fmaxf(ymax, fmaxf(fabsf(y[i]), fabsf(y[i + 1])));
+                uint32_t h;
+                if (pl == 0) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(y[i + 1]), "f"(y[i]));
+                else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(y[i + 1]), "f"(y[i]));
+                w[i >> 1] = h;
                 if (pl == 0) {
-                  // the high plane saturates at the fp16 range: flagged, never silent (yolo_check_saturation)
-                  if (i < nvalid && fmaxf(fabsf(a), fabsf(b)) > kF16Max) saturated = 1;      // columns >= nvalid hold stale TMEM, never stored
-                  a = fminf(fmaxf(a, -kF16Max), kF16Max); b = fminf(fmaxf(b, -kF16Max), kF16Max);
-                }
-                __half2 h = __floats2half2_rn(a, b);
-                w[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
-                if (pl == 0) {
-                  float2 f = __half22float2(h);
+                  float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
                   y[i] = y[i] - f.x; y[i + 1] = y[i + 1] - f.y;     // exact: remainder has <= 13 bits
                 }
               } else {
@@ -582,16 +606,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (pl + 1 < NP) { y[i] -= ha; y[i + 1] -= hb; }
               }
             }
-            for (int q = 0; q < npix && !p.dbg_nostore; ++q) {
-              uint4* op = reinterpret_cast<uint4*>(static_cast<unsigned short*>(p.out) + (size_t)pl * p.out_plane_stride +
-                                                   pix[q] * p.out_cpitch + p.out_coff + nb);
+            // transpose through the warp's staging rows (16-byte chunk g of row r sits at chunk g ^ ((r >> 1) & 3): conflict-free)
+            __syncwarp();
+            {
+              const int sw = (lane >> 1) & 3;
 #pragma unroll
               for (int g = 0; g < 4; ++g)
-                if (g * 8 < nvalid) op[g] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);   // Cout % 8 == 0
+                *reinterpret_cast<uint4*>(s_stage + lane * 64 + ((g ^ sw) << 4)) = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+            }
+            __syncwarp();
+            {
+              const int g = lane & 3;
+              unsigned short* obase = static_cast<unsigned short*>(p.out) + (size_t)pl * p.out_plane_stride + p.out_coff + nb + g * 8;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = (lane >> 2) + 8 * i;
+                const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 64 + ((g ^ ((r >> 1) & 3)) << 4));
+                if (rvalid[i] && g * 8 < nvalid) {                              // Cout % 8 == 0
+                  *reinterpret_cast<uint4*>(obase + (size_t)rpix[i] * p.out_cpitch) = v;
+                  if (p.upsample2 == 1) {                                        // nearest 2x upsampling: three more copies
+                    *reinterpret_cast<uint4*>(obase + (size_t)(rpix[i] + 1) * p.out_cpitch) = v;
+                    *reinterpret_cast<uint4*>(obase + (size_t)(rpix[i] + 2 * p.Wo) * p.out_cpitch) = v;
+                    *reinterpret_cast<uint4*>(obase + (size_t)(rpix[i] + 2 * p.Wo + 1) * p.out_cpitch) = v;
+                  }
+                }
+              }
             }
           }
         }
       }
+      if (ymax > kF16Max) saturated = 1;
     }
     if (saturated && p.sat_flag) atomicOr(p.sat_flag, YOLO_SAT_ACT_CONV);
   }
@@ -1060,7 +1104,7 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, Umma
   }
   if (u.c32i) kind = 7;
   const int stage_bytes = kind == 7 ? TILE_M * p.bk * 2 + np * p.BN * p.bk * 2 : np * (TILE_M * p.bk * 2 + (kind == 6 ? p.BN / 2 : p.BN) * p.bk * 2);
-  const int aux_bytes = 16 * MAX_STAGES + 128 + 2 * 2 * p.BN * 4 + 64;
+  const int aux_bytes = 16 * MAX_STAGES + 128 + 2 * 2 * p.BN * 4 + 64 + 128 + 8 * STAGE_OUT_BYTES;
   // 8 MMAs of the leading product per TMEM partial.  Longer partials are ~3 % faster but their truncation bias is
   // systematic (same sign on every output) and compounds through the layers: flush 8 -> Darknet-53 head error 6.6e-4
   // instead of 2.9e-4 (profiles/r1_parity_report.txt).  Env YOLO_B200_FLUSH overrides for experiments.
