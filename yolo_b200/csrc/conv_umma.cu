@@ -379,6 +379,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const float acc_scale = p.acc_scale * (p.acc_scale_dev ? __ldg(p.acc_scale_dev) : 1.f);
     int saturated = 0;
     int it = WIDE ? 0 : group;
+    int staged_nt = -1;
     // Accumulation turns.  An mbarrier parity wait can only tell "this phase" from "the previous one", so a group must
     // not start waiting for its partials before the other group has consumed all of the preceding tile's partials:
     // named barriers 3/4 pass the turn (FA3-style ping-pong); group 1 donates the first turn to group 0.
@@ -387,15 +388,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
       const int m0 = (PAIR ? mt * 2 + (int)cta_rank : mt) * TILE_M;
       const int n0 = nt * p.BN + (WIDE ? group * 128 : 0);
-      // stage scale/shift of this tile's columns (the group's previous tile is completely finished here)
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
-      for (int i = et; i < gcols; i += GROUP_THREADS) {
-        const int n = n0 + i;
-        // the accumulator scale is a power of two (weight pre-scale, dynamic gradient scale): folding it into the BN scale is exact
-        s_scale[i] = ((p.scale && n < p.Cout) ? __ldg(p.scale + n) : 1.f) * acc_scale;
-        s_scale[gcols + i] = (p.shift && n < p.Cout) ? __ldg(p.shift + n) : 0.f;
+      // stage scale/shift of this tile's columns (the group's previous tile is completely finished here); a group that stays on
+      // the same column block keeps what it staged
+      if (nt != staged_nt) {
+        staged_nt = nt;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+        for (int i = et; i < gcols; i += GROUP_THREADS) {
+          const int n = n0 + i;
+          // the accumulator scale is a power of two (weight pre-scale, dynamic gradient scale): folding it into the BN scale is exact
+          s_scale[i] = ((p.scale && n < p.Cout) ? __ldg(p.scale + n) : 1.f) * acc_scale;
+          s_scale[gcols + i] = (p.shift && n < p.Cout) ? __ldg(p.shift + n) : 0.f;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
 
       float acc[4][32];
 #pragma unroll
