@@ -534,35 +534,39 @@ __device__ __forceinline__ unsigned long long dup2(float x) {
 // shared-memory variant (profiles/r2_ncu_stem.txt) - only carries the input patch and the staged results.  Training reads the master
 // weights from the flat device buffer and keeps the shared-memory variant.
 constexpr int STEM_TH = 16;
-struct StemWeights { float w[27 * 32]; };
-template <class FO, int LAYOUT, int CO, int PX, bool WCONST>
-__global__ void __launch_bounds__(256, PX == 2 ? 2 : 4) stem3x3_tile_kernel(const __grid_constant__ ConvKArgs args, const __grid_constant__ StemWeights wp) {
+template <int N>
+struct StemWeights { float w[N]; int co_off; };               // [KS*KS*3][CO] slice of the weight matrix for output channels [co_off, co_off + CO)
+template <class FO, int LAYOUT, int CO, int PX, bool WCONST, int KS, int STRIDE>
+__global__ void __launch_bounds__(256, PX == 2 ? 2 : 4)
+stem_tile_kernel(const __grid_constant__ ConvKArgs args, const __grid_constant__ StemWeights<WCONST ? KS * KS * 3 * CO : 1> wp) {
   using TOut = typename FO::T;
-  constexpr int TW = 16 * PX, IW = (TW + 2) * 3;
-  constexpr int IPITCH = PX == 2 ? 112 : 80;                       // >= IW and = 16 mod 32: the two tile rows of a warp hit disjoint banks
+  constexpr int TW = 16 * PX, TAPS = KS * KS * 3;
+  constexpr int PH = (STEM_TH - 1) * STRIDE + KS, PW = (TW - 1) * STRIDE + KS, IW = PW * 3;
+  constexpr int IPITCH = ((IW + 15) / 32) * 32 + 16;               // >= IW and = 16 mod 32: the two tile rows of a warp hit disjoint banks (stride 1)
   const ConvDesc& d = args.d;
-  extern __shared__ __align__(16) float s_w[];                     // [27][CO], scale[CO], shift[CO], patch[18][IPITCH], staged out
-  float* s_sc = s_w + 27 * CO;
+  extern __shared__ __align__(16) float s_w[];                     // [TAPS][CO] (shared-memory variant), scale[CO], shift[CO], patch[PH][IPITCH], staged out
+  float* s_sc = s_w + (WCONST ? 0 : TAPS * CO);
   float* s_sh = s_sc + CO;
   float* s_in = s_sh + CO;
-  TOut* s_out = reinterpret_cast<TOut*>(s_in + (STEM_TH + 2) * IPITCH);               // [NP][256*PX][CO]
+  TOut* s_out = reinterpret_cast<TOut*>(s_in + PH * IPITCH);       // [NP][256*PX][CO]
   const int tid = threadIdx.x;
+  const int co_off = WCONST ? wp.co_off : 0;
   const int tiles_w = (d.Wo + TW - 1) / TW, tiles_h = (d.Ho + STEM_TH - 1) / STEM_TH;
   const int tw = blockIdx.x % tiles_w, th = (blockIdx.x / tiles_w) % tiles_h, n = blockIdx.x / (tiles_w * tiles_h);
   const int oh0 = th * STEM_TH, ow0 = tw * TW;
   if (!WCONST)
-    for (int i = tid; i < 27 * CO; i += 256) s_w[i] = __ldg(d.w_f32 + i);
+    for (int i = tid; i < TAPS * CO; i += 256) s_w[i] = __ldg(d.w_f32 + i);
   for (int i = tid; i < CO; i += 256) {
-    s_sc[i] = d.scale ? __ldg(d.scale + i) : 1.f;
-    s_sh[i] = d.shift ? __ldg(d.shift + i) : 0.f;
+    s_sc[i] = d.scale ? __ldg(d.scale + co_off + i) : 1.f;
+    s_sh[i] = d.shift ? __ldg(d.shift + co_off + i) : 0.f;
   }
-  for (int i = tid; i < (STEM_TH + 2) * IW; i += 256) {
+  for (int i = tid; i < PH * IW; i += 256) {
     const int row = i / IW, rem = i - row * IW;
-    const int ih = oh0 - 1 + row;
+    const int ih = oh0 * STRIDE - d.pad + row;
     int col, c;
-    if (LAYOUT == IN_NCHW_F32) { c = rem / (TW + 2); col = rem - c * (TW + 2); }                // column fastest: coalesced per channel plane
+    if (LAYOUT == IN_NCHW_F32) { c = rem / PW; col = rem - c * PW; }                            // column fastest: coalesced per channel plane
     else { col = rem / 3; c = rem - col * 3; }                                                  // byte order of the camera frame
-    const int iw = ow0 - 1 + col;
+    const int iw = ow0 * STRIDE - d.pad + col;
     float v = 0.f;
     if ((unsigned)ih < (unsigned)d.H && (unsigned)iw < (unsigned)d.W) {
       if (LAYOUT == IN_NCHW_F32) v = __ldg(static_cast<const float*>(d.in) + ((size_t)(n * 3 + c) * d.H + ih) * d.W + iw);
@@ -577,16 +581,18 @@ __global__ void __launch_bounds__(256, PX == 2 ? 2 : 4) stem3x3_tile_kernel(cons
   for (int p = 0; p < PX; ++p)
 #pragma unroll
     for (int j = 0; j < CO / 2; ++j) acc[p][j] = 0ull;
+  // filter rows: unrolled for the 3x3 stem; a real loop for 7x7 (147 taps x 16 FFMA2 would be 60 KB of straight-line code) - the
+  // row index is warp-uniform, so the constant-bank weights are still fetched through uniform registers
+#pragma unroll(KS <= 3 ? KS : 1)
+  for (int r = 0; r < KS; ++r) {
+    const float* row = s_in + (ty * STRIDE + r) * IPITCH + tx * STRIDE * 3;
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const float* row = s_in + (ty + r) * IPITCH + tx * 3;
-#pragma unroll
-    for (int qc = 0; qc < 9; ++qc) {                                // (q, c) in the order of the weight rows: k = (r*3 + q)*3 + c
+    for (int qc = 0; qc < KS * 3; ++qc) {                           // (q, c) in the order of the weight rows: k = (r*KS + q)*3 + c
       unsigned long long x[PX];
 #pragma unroll
-      for (int p = 0; p < PX; ++p) x[p] = dup2(row[p * 16 * 3 + qc]);
-      const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(s_w + (r * 9 + qc) * CO);
-      const unsigned long long* wc = reinterpret_cast<const unsigned long long*>(wp.w) + (r * 9 + qc) * (CO / 2);
+      for (int p = 0; p < PX; ++p) x[p] = dup2(row[p * 16 * STRIDE * 3 + qc]);
+      const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(s_w + (r * KS * 3 + qc) * CO);
+      const unsigned long long* wc = reinterpret_cast<const unsigned long long*>(wp.w) + (r * KS * 3 + qc) * (CO / 2);
 #pragma unroll
       for (int j = 0; j < CO / 4; ++j) {
         ulonglong2 w;
@@ -631,7 +637,7 @@ __global__ void __launch_bounds__(256, PX == 2 ? 2 : 4) stem3x3_tile_kernel(cons
 #pragma unroll
   for (int q = 0; q < FO::NP; ++q) {
     const uint4* src = reinterpret_cast<const uint4*>(s_out + (size_t)q * BLK_PIX * CO);
-    TOut* dst = static_cast<TOut*>(d.out) + (size_t)q * d.out_plane_stride + d.out_coff;
+    TOut* dst = static_cast<TOut*>(d.out) + (size_t)q * d.out_plane_stride + d.out_coff + co_off;
     for (int i = tid; i < BLK_PIX * SW_VPP; i += 256) {
       const int pix = i / SW_VPP, vi = i - pix * SW_VPP;
       const int oh = oh0 + pix / TW, ow = ow0 + pix % TW;
@@ -642,37 +648,48 @@ __global__ void __launch_bounds__(256, PX == 2 ? 2 : 4) stem3x3_tile_kernel(cons
   }
 }
 
-template <class FO, int CO, int PX>
+template <class FO, int CO, int PX, int KS, int STRIDE>
 static int launch_stem_tile_t(const ConvKArgs& a, int in_layout, cudaStream_t st) {
   const ConvDesc& d = a.d;
-  constexpr int TW = 16 * PX, IPITCH = PX == 2 ? 112 : 80;
-  const int smem = (27 * CO + 2 * CO + (STEM_TH + 2) * IPITCH) * 4 + FO::NP * STEM_TH * TW * CO * (int)sizeof(typename FO::T);
+  constexpr int TW = 16 * PX, TAPS = KS * KS * 3;
+  constexpr int PH = (STEM_TH - 1) * STRIDE + KS, PW = (TW - 1) * STRIDE + KS, IW = PW * 3, IPITCH = ((IW + 15) / 32) * 32 + 16;
+  const int out_bytes = FO::NP * STEM_TH * TW * CO * (int)sizeof(typename FO::T);
   const int blocks = d.N * ((d.Ho + STEM_TH - 1) / STEM_TH) * ((d.Wo + TW - 1) / TW);
-  StemWeights wp;
   static const bool const_off = [] { const char* e = getenv("YOLO_B200_STEM_WCONST"); return e && e[0] == '0'; }();
-  if (d.w_host && !const_off) {                                 // [27][CO] rows (cout_pad == Cout is part of stem_eligible)
-    memcpy(wp.w, d.w_host, sizeof(float) * 27 * CO);
-    int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_tile_kernel<FO, IN_NCHW_F32, CO, PX, true>), 160 * 1024);
-    if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_tile_kernel<FO, IN_NHWC_U8, CO, PX, true>), 160 * 1024);
+  if (d.w_host && !const_off) {
+    const int smem = (2 * CO + PH * IPITCH) * 4 + out_bytes;
+    int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem_tile_kernel<FO, IN_NCHW_F32, CO, PX, true, KS, STRIDE>), 160 * 1024);
+    if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem_tile_kernel<FO, IN_NHWC_U8, CO, PX, true, KS, STRIDE>), 160 * 1024);
     if (rc) return rc;
-    if (in_layout == IN_NCHW_F32) stem3x3_tile_kernel<FO, IN_NCHW_F32, CO, PX, true><<<blocks, 256, smem, st>>>(a, wp);
-    else stem3x3_tile_kernel<FO, IN_NHWC_U8, CO, PX, true><<<blocks, 256, smem, st>>>(a, wp);
+    StemWeights<TAPS * CO> wp;
+    for (int co = 0; co < d.Cout; co += CO) {                     // one launch per CO output channels (the 64-channel 7x7 stem: two)
+      for (int k = 0; k < TAPS; ++k) memcpy(wp.w + k * CO, d.w_host + (size_t)k * d.cout_pad + co, sizeof(float) * CO);
+      wp.co_off = co;
+      if (in_layout == IN_NCHW_F32) stem_tile_kernel<FO, IN_NCHW_F32, CO, PX, true, KS, STRIDE><<<blocks, 256, smem, st>>>(a, wp);
+      else stem_tile_kernel<FO, IN_NHWC_U8, CO, PX, true, KS, STRIDE><<<blocks, 256, smem, st>>>(a, wp);
+      if (co) ++g_launches;
+    }
     return YOLO_OK;
   }
-  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_tile_kernel<FO, IN_NCHW_F32, CO, PX, false>), 160 * 1024);
-  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem3x3_tile_kernel<FO, IN_NHWC_U8, CO, PX, false>), 160 * 1024);
+  if (d.Cout != CO) return fail(YOLO_E_UNSUPPORTED, "stem: the shared-memory-weights variant takes Cout == %d", CO);
+  const int smem = (TAPS * CO + 2 * CO + PH * IPITCH) * 4 + out_bytes;
+  StemWeights<1> none;
+  none.co_off = 0;
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem_tile_kernel<FO, IN_NCHW_F32, CO, PX, false, KS, STRIDE>), 160 * 1024);
+  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(&stem_tile_kernel<FO, IN_NHWC_U8, CO, PX, false, KS, STRIDE>), 160 * 1024);
   if (rc) return rc;
-  if (in_layout == IN_NCHW_F32) stem3x3_tile_kernel<FO, IN_NCHW_F32, CO, PX, false><<<blocks, 256, smem, st>>>(a, wp);
-  else stem3x3_tile_kernel<FO, IN_NHWC_U8, CO, PX, false><<<blocks, 256, smem, st>>>(a, wp);
+  if (in_layout == IN_NCHW_F32) stem_tile_kernel<FO, IN_NCHW_F32, CO, PX, false, KS, STRIDE><<<blocks, 256, smem, st>>>(a, none);
+  else stem_tile_kernel<FO, IN_NHWC_U8, CO, PX, false, KS, STRIDE><<<blocks, 256, smem, st>>>(a, none);
   return YOLO_OK;
 }
 template <class FO>
 static int launch_stem_tile(const ConvKArgs& a, int in_layout, cudaStream_t st) {
   // one pixel per thread: 64 registers and 40 KB per block -> four blocks per SM hide the load and store phases of each other
   // (two pixels per thread reuse every weight load twice but fit one or two blocks: YOLO_B200_STEM_PX=2, measured slower)
+  if (a.d.kh == 7) return launch_stem_tile_t<FO, 32, 1, 7, 2>(a, in_layout, st);      // DenseNet stem: 7x7 / 2, 64 channels in two halves
   static const bool px2 = [] { const char* e = getenv("YOLO_B200_STEM_PX"); return e && e[0] == '2'; }();
-  if (px2) return a.d.Cout == 32 ? launch_stem_tile_t<FO, 32, 2>(a, in_layout, st) : launch_stem_tile_t<FO, 16, 2>(a, in_layout, st);
-  return a.d.Cout == 32 ? launch_stem_tile_t<FO, 32, 1>(a, in_layout, st) : launch_stem_tile_t<FO, 16, 1>(a, in_layout, st);
+  if (px2) return a.d.Cout == 32 ? launch_stem_tile_t<FO, 32, 2, 3, 1>(a, in_layout, st) : launch_stem_tile_t<FO, 16, 2, 3, 1>(a, in_layout, st);
+  return a.d.Cout == 32 ? launch_stem_tile_t<FO, 32, 1, 3, 1>(a, in_layout, st) : launch_stem_tile_t<FO, 16, 1, 3, 1>(a, in_layout, st);
 }
 
 template <class FO, int PX>
@@ -687,10 +704,16 @@ static int launch_stem_t(const ConvKArgs& a, int in_layout, int smem, cudaStream
   return YOLO_OK;
 }
 
+static bool stem7_eligible(const ConvDesc& d) {           // DenseNet stem (7x7 / 2 / pad 3, 64 channels): tiled kernel with kernel-parameter weights only
+  return d.kh == 7 && d.kw == 7 && d.stride == 2 && d.pad == 3 && d.Cout % 32 == 0 && d.Cout <= 64 && d.w_host != nullptr &&
+         d.out_dtype != DT_F32 && d.out_dtype != DT_BF16X3;
+}
 bool stem_eligible(const ConvDesc& d, int in_layout) {
-  return (in_layout == IN_NCHW_F32 || in_layout == IN_NHWC_U8) && d.Cin == 3 && d.kh == 3 && d.kw == 3 && d.Cout % STEM_CO == 0 &&
-         d.Cout <= 32 && !d.res && !d.pre_scale && !d.upsample2 && !d.out_nchw && ((d.out_cpitch | d.out_coff) & 7) == 0 &&
-         d.cout_pad == d.Cout;
+  if (!((in_layout == IN_NCHW_F32 || in_layout == IN_NHWC_U8) && d.Cin == 3 && !d.res && !d.pre_scale && !d.upsample2 && !d.out_nchw &&
+        ((d.out_cpitch | d.out_coff) & 7) == 0 && d.cout_pad == d.Cout))
+    return false;
+  if (stem7_eligible(d)) return true;
+  return d.kh == 3 && d.kw == 3 && d.Cout % STEM_CO == 0 && d.Cout <= 32;
 }
 
 int launch_stem(const ConvDesc& d, int in_layout, cudaStream_t st) {
@@ -698,14 +721,15 @@ int launch_stem(const ConvDesc& d, int in_layout, cudaStream_t st) {
   a.d = d;
   a.in_layout = in_layout;
   a.M = d.N * d.Ho * d.Wo;
-  a.K = 27;
+  a.K = d.kh * d.kw * 3;
   const int esz = d.out_dtype == DT_F32 ? 4 : 2, npl = dtype_planes(d.out_dtype);
   auto smem_for = [&](int px) { return (27 * d.cout_pad + 2 * d.Cout) * 4 + npl * 256 * px * d.Cout * esz; };   // weights, scale/shift, staged rows
   const bool two = smem_for(2) <= 150 * 1024;                 // two pixels per thread whenever the staged rows fit
   int rc;
   static const bool tile_off = [] { const char* e = getenv("YOLO_B200_STEM_TILE"); return e && e[0] == '0'; }();
   const size_t osz = (size_t)esz;
-  const bool tiled = !tile_off && d.stride == 1 && d.pad == 1 && d.Ho == d.H && d.Wo == d.W && (d.Cout == 16 || d.Cout == 32) &&
+  const bool k7 = stem7_eligible(d);
+  const bool tiled = ((!tile_off && d.kh == 3 && d.stride == 1 && d.pad == 1 && d.Ho == d.H && d.Wo == d.W && (d.Cout == 16 || d.Cout == 32)) || k7) &&
                      (d.Cout * osz) % 16 == 0 && (d.out_cpitch * osz) % 16 == 0 && (d.out_coff * osz) % 16 == 0 &&
                      ((size_t)d.out_plane_stride * osz) % 16 == 0 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0;
   if (tiled) {
@@ -720,6 +744,7 @@ int launch_stem(const ConvDesc& d, int in_layout, cudaStream_t st) {
     YB_CUDA(cudaGetLastError());
     return YOLO_OK;
   }
+  if (k7) return fail(YOLO_E_UNSUPPORTED, "stem: 7x7 stem output slices must be 16-byte aligned");
   switch (d.out_dtype) {
     case DT_F32: rc = two ? launch_stem_t<FmtF32, 2>(a, in_layout, smem_for(2), st) : launch_stem_t<FmtF32, 1>(a, in_layout, smem_for(1), st); break;
     case DT_BF16: rc = two ? launch_stem_t<FmtBF16, 2>(a, in_layout, smem_for(2), st) : launch_stem_t<FmtBF16, 1>(a, in_layout, smem_for(1), st); break;
@@ -761,6 +786,46 @@ __global__ void pool_kernel(const typename F::T* __restrict__ in, typename F::T*
   }
 }
 
+// eight channels per thread (16-byte loads per plane) when the channel slices allow it: the scalar kernel above issues one 2-byte
+// load per plane, tap and element (DenseNet stem max-pool at 160 x 256 x 64, batch 64: 1.02 ms -> the vector kernel)
+template <class F, bool IS_MAX>
+__global__ void __launch_bounds__(256)
+pool_vec8_kernel(const typename F::T* __restrict__ in, typename F::T* __restrict__ out, int N, int H, int W, int C, int in_cpitch, int in_coff,
+                 long long in_ps, int out_cpitch, int out_coff, long long out_ps, int Ho, int Wo, int k, int stride, int pad) {
+  const int c8 = C >> 3;
+  const size_t total = (size_t)N * Ho * Wo * c8;
+  int sat = 0;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c8) * 8;
+    const size_t pix = idx / c8;
+    const int ow = (int)(pix % Wo);
+    const size_t t = pix / Wo;
+    const int oh = (int)(t % Ho), n = (int)(t / Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = IS_MAX ? -CUDART_INF_F : 0.f;
+    for (int r = 0; r < k; ++r) {
+      const int ih = oh * stride - pad + r;
+      if ((unsigned)ih >= (unsigned)H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int iw = ow * stride - pad + s;
+        if ((unsigned)iw >= (unsigned)W) continue;
+        float v[8];
+        load8f<F>(in + ((size_t)(n * H + ih) * W + iw) * in_cpitch + in_coff + c, in_ps, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = IS_MAX ? fmaxf(acc[j], v[j]) : acc[j] + v[j];
+      }
+    }
+    if (!IS_MAX) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] / (float)(k * k);
+    }
+    typename F::T* op = out + pix * out_cpitch + out_coff + c;
+    store4f<F>(op, out_ps, acc, sat);
+    store4f<F>(op + 4, out_ps, acc + 4, sat);
+  }
+}
+
 int launch_pool(const void* in, void* out, int dtype, int N, int H, int W, int C, int in_cpitch, int in_coff,
                 long long in_plane_stride, int out_cpitch, int out_coff, long long out_plane_stride, int k, int stride, int pad,
                 int is_max, cudaStream_t st) {
@@ -769,6 +834,23 @@ int launch_pool(const void* in, void* out, int dtype, int N, int H, int W, int C
   if (total == 0) return fail(YOLO_E_SHAPE, "pool: empty problem");
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
+  const bool vec8 = dtype != DT_F32 && C % 8 == 0 && ((in_cpitch | in_coff | out_cpitch | out_coff) & 7) == 0 && in_plane_stride % 8 == 0 &&
+                    out_plane_stride % 8 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (vec8) {
+    blocks = (int)((total / 8 + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+#define YB_POOLV(F, MX)                                                                                                         \
+  pool_vec8_kernel<F, MX><<<blocks, 256, 0, st>>>(static_cast<const F::T*>(in), static_cast<F::T*>(out), N, H, W, C, in_cpitch, \
+                                                  in_coff, in_plane_stride, out_cpitch, out_coff, out_plane_stride, Ho, Wo, k, stride, pad)
+    if (dtype == DT_BF16) { if (is_max) YB_POOLV(FmtBF16, true); else YB_POOLV(FmtBF16, false); }
+    else if (dtype == DT_BF16X3) { if (is_max) YB_POOLV(FmtBF16X3, true); else YB_POOLV(FmtBF16X3, false); }
+    else { if (is_max) YB_POOLV(FmtF16X2, true); else YB_POOLV(FmtF16X2, false); }
+#undef YB_POOLV
+    ++g_launches;
+    YB_CUDA(cudaGetLastError());
+    return YOLO_OK;
+  }
 #define YB_POOL(F, MX)                                                                                                   \
   pool_kernel<F, MX><<<blocks, 256, 0, st>>>(static_cast<const F::T*>(in), static_cast<F::T*>(out), N, H, W, C, in_cpitch, \
                                              in_coff, in_plane_stride, out_cpitch, out_coff, out_plane_stride, Ho, Wo, k, stride, pad)
@@ -786,7 +868,7 @@ int launch_pool(const void* in, void* out, int dtype, int N, int H, int W, int C
 // In a dense block every layer applies ITS OWN BatchNorm to the shared concatenated features, so the activation cannot be folded into
 // the producer's epilogue.  The FFMA kernel applies it while gathering; the tensor-core kernel stages raw tiles by TMA, so the
 // pre-activated input is materialised once per layer (channel-padded to the K step with zeros) and the convolution runs unmodified.
-template <class F>
+template <class F, bool ALIGNED>
 __global__ void __launch_bounds__(256)
 preact_kernel(const typename F::T* __restrict__ in, typename F::T* __restrict__ out, long long pixels, int C, int Cpad, int in_cpitch, int in_coff,
               long long in_ps, int out_cpitch, long long out_ps, const float* __restrict__ scale, const float* __restrict__ shift, int* sat_flag) {
@@ -797,13 +879,23 @@ preact_kernel(const typename F::T* __restrict__ in, typename F::T* __restrict__ 
     const long long m = i / oct;
     const int c = (int)(i - m * oct) * 8;
     float v[8];
-    if (c < C) {
-      load8f<F>(in + m * in_cpitch + in_coff + c, in_ps, v);
+    if (ALIGNED) {
+      if (c < C) {
+        load8f<F>(in + m * in_cpitch + in_coff + c, in_ps, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], __ldg(scale + c + j), __ldg(shift + c + j)), 0.f);
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], __ldg(scale + c + j), __ldg(shift + c + j)), 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
     } else {
+      // concat buffers whose channel count is not a multiple of 8 (DenseNet block 4 starts at 260 channels): element loads; the copy
+      // this pass writes is aligned, which is what puts the convolution behind it on the tensor cores
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const int cj = c + j;
+        v[j] = cj < C ? fmaxf(fmaf(ld1f<F>(in + m * in_cpitch + in_coff + cj, in_ps), __ldg(scale + cj), __ldg(shift + cj)), 0.f) : 0.f;
+      }
     }
     store4f<F>(out + m * out_cpitch + c, out_ps, v, sat);
     store4f<F>(out + m * out_cpitch + c + 4, out_ps, v + 4, sat);
@@ -813,12 +905,18 @@ preact_kernel(const typename F::T* __restrict__ in, typename F::T* __restrict__ 
 
 int launch_preact(const void* in, void* out, int dtype, long long pixels, int C, int Cpad, int in_cpitch, int in_coff, long long in_plane_stride,
                   int out_cpitch, long long out_plane_stride, const float* scale, const float* shift, int* sat_flag, cudaStream_t st) {
-  if (C % 8 || Cpad % 8 || in_cpitch % 8 || in_coff % 8 || out_cpitch % 8 || dtype == DT_F32) return fail(YOLO_E_UNSUPPORTED, "preact: needs 16-bit planes and channel counts % 8 == 0");
+  if (Cpad % 8 || out_cpitch % 8 || out_plane_stride % 8 || dtype == DT_F32) return fail(YOLO_E_UNSUPPORTED, "preact: needs 16-bit planes and a padded channel count % 8 == 0");
+  const bool aligned = C % 8 == 0 && in_cpitch % 8 == 0 && in_coff % 8 == 0 && in_plane_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
   const long long total = pixels * (Cpad / 8);
   if (total <= 0) return fail(YOLO_E_SHAPE, "preact: empty problem");
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-#define YB_PREACT(F) preact_kernel<F><<<blocks, 256, 0, st>>>(static_cast<const F::T*>(in), static_cast<F::T*>(out), pixels, C, Cpad, in_cpitch, in_coff, \
-                                                             in_plane_stride, out_cpitch, out_plane_stride, scale, shift, sat_flag)
+#define YB_PREACT(F)                                                                                                                             \
+  do {                                                                                                                                           \
+    if (aligned) preact_kernel<F, true><<<blocks, 256, 0, st>>>(static_cast<const F::T*>(in), static_cast<F::T*>(out), pixels, C, Cpad, in_cpitch, \
+                                                                in_coff, in_plane_stride, out_cpitch, out_plane_stride, scale, shift, sat_flag);  \
+    else preact_kernel<F, false><<<blocks, 256, 0, st>>>(static_cast<const F::T*>(in), static_cast<F::T*>(out), pixels, C, Cpad, in_cpitch,       \
+                                                         in_coff, in_plane_stride, out_cpitch, out_plane_stride, scale, shift, sat_flag);         \
+  } while (0)
   if (dtype == DT_BF16) YB_PREACT(FmtBF16);
   else if (dtype == DT_BF16X3) YB_PREACT(FmtBF16X3);
   else YB_PREACT(FmtF16X2);

@@ -165,7 +165,7 @@ struct Builder {
   // weights; otherwise the FFMA kernel applies the prologue while gathering.
   View preact_conv(const std::string& wname, const View& in, View& scratch, int cout, int k, int pad, int act, const std::string& bn,
                    const std::string& bias, const std::string& prebn, const View* dst = nullptr) {
-    const bool tc = h->act_dtype != DT_F32 && in.C % 8 == 0 && in.cpitch % 8 == 0 && in.coff % 8 == 0 && scratch.buf >= 0;
+    const bool tc = h->act_dtype != DT_F32 && scratch.buf >= 0;      // the pass itself copes with unaligned concat slices
     if (!tc) return conv("", wname, in, cout, k, pad, 1, act, bn, bias, prebn, dst);
     const int cpad = (in.C + 63) & ~63;
     Op op;
@@ -541,7 +541,8 @@ extern "C" int yolo_finalize_params(yolo_handle* h, void* stream) {
             wd[((size_t)(r * kw + s2) * cin + c) * op.cout_pad + o] = W[(((size_t)o * creal + c) * kh + r) * kw + s2];
     op.w_f32 = op.w_f32_own = reinterpret_cast<float*>(dbase + slots[i].w);
     op.w_stem_host.clear();
-    if (cin == 3 && kh == 3 && kw == 3 && cout <= 32 && op.cout_pad == cout) op.w_stem_host.assign(wd, wd + (size_t)27 * op.cout_pad);
+    if (cin == 3 && ((kh == 3 && kw == 3 && cout <= 32) || (kh == 7 && kw == 7 && cout <= 64)) && op.cout_pad == cout)
+      op.w_stem_host.assign(wd, wd + (size_t)kh * kw * 3 * op.cout_pad);
     std::vector<float> sc, sh;
     op.scale = op.shift = op.pre_scale = op.pre_shift = nullptr;
     if (op.p_bn >= 0) {
