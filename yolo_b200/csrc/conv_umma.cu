@@ -119,6 +119,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 //      which cost twice as much per byte to land).  One k-block = one filter tap, K' = 64: weight plane X = [w_hi | w_hi] gives hi*hi
 //      (k-steps 0,1 -> partial) and lo*hi (k-steps 2,3 -> correction), plane Y = [w_lo | 0] gives hi*lo (k-steps 0,1 -> correction).
 template <int MODE, bool OUT_F32, int KIND, bool STATS>
+// (168 registers: ten warps put three on a scheduler's 16K-register file)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ UmmaParams p) {
@@ -466,11 +467,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // once per tile for the four rows a lane stores.
       bool rvalid[4];
       int rpix[4];
-      if (!OUT_F32) {
+      {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int mr = m0 + lane_grp * 32 + (lane >> 2) + 8 * i;
-          rvalid[i] = mr < p.M && p.dbg_nostore == 0;
+          rvalid[i] = mr < p.M && (OUT_F32 ? p.dbg_nostore != 2 : p.dbg_nostore == 0);
           if (p.upsample2) {
             const int img = mr / HoWo, rem = mr - img * HoWo;
             const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
@@ -502,6 +503,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (nb >= p.Cout) break;
         float* y = acc[0];
         const int nvalid = min(32, p.Cout - nb);
+        // fp32 outputs with 16-byte aligned, whole 32-column chunks (every data-gradient buffer) use the same per-warp transpose as the
+        // 16-bit formats, 16 columns at a time.  Accumulation (out += result: a gradient range with an earlier producer) is a vector
+        // reduction at the L2 (red.global.add.v4.f32): no operand load, no latency, and still deterministic - every element receives
+        // exactly one addend per launch, launches are stream-ordered, and a two-operand fp32 add does not depend on order
+        const bool f32_tr = OUT_F32 && ((p.out_cpitch | p.out_coff) & 3) == 0 && nvalid == 32;
         {
           const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
           const float4* sh4 = reinterpret_cast<const float4*>(s_scale + gcols + c0);
@@ -540,15 +546,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         if (OUT_F32) {                                      // head convs: fp32 NHWC == (B, H*W, A, C); gradient buffers (accum)
           float* op = static_cast<float*>(p.out) + pix0 * p.out_cpitch + p.out_coff + nb;
-          if (!valid) {
-            // rows past the last pixel: nothing to store
-          } else if (((p.out_cpitch | p.out_coff) & 3) == 0 && nvalid == 32) {
+          if (f32_tr) {
+            const int g = lane & 3, sw = (lane >> 1) & 3;
+            float* obase = static_cast<float*>(p.out) + p.out_coff + nb + g * 4;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 v = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
-              if (p.accum) { const float4 o = *reinterpret_cast<const float4*>(op + i); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-              *reinterpret_cast<float4*>(op + i) = v;
+            for (int hh = 0; hh < 2; ++hh) {
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(s_stage + lane * 64 + ((q ^ sw) << 4)) =
+                    make_float4(y[hh * 16 + 4 * q], y[hh * 16 + 4 * q + 1], y[hh * 16 + 4 * q + 2], y[hh * 16 + 4 * q + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = (lane >> 2) + 8 * i;
+                const float4 v = *reinterpret_cast<const float4*>(s_stage + r * 64 + ((g ^ ((r >> 1) & 3)) << 4));
+                float* dst = obase + (size_t)rpix[i] * p.out_cpitch + hh * 16;
+                if (!rvalid[i]) continue;
+                if (p.accum) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                else *reinterpret_cast<float4*>(dst) = v;
+              }
             }
+          } else if (!valid) {
+            // rows past the last pixel: nothing to store
           } else if (((p.out_cpitch | p.out_coff) & 1) == 0) {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {

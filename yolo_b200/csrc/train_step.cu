@@ -290,27 +290,29 @@ __device__ __forceinline__ void load_dy8(const float* dy, int dy_cpitch, int dy_
   } else ld8_f32(dy + (size_t)m * dy_cpitch + dy_coff + c, g);
 }
 
-// Reduction pass of the BatchNorm backward: per channel sum g and sum g*xhat with g = dy * act'(u) (fixed-order slabs -> slab[y][q][C]),
-// the layer's max|g| (for the dz scale) and the residual's gradient (y = act(bn(z)) + res  ->  d res += dy).
-// Block = (256 / octs) row lanes x octs channel octets over <= 256 channels; grid = (channel blocks, slabs).
-__global__ void __launch_bounds__(256)
+// Reduction pass of the BatchNorm backward: per channel sum g and sum g*z with g = dy * act'(u) (fixed-order slabs -> slab[y][q][C]; the
+// finalize kernel centres the second moment in double: sum g*xhat = rstd * (sum g*z - mean * sum g)), the layer's max|g| (for the dz
+// scale) and the residual's gradient (y = act(bn(z)) + res  ->  d res += dy).
+// Block = (256 / octs) row lanes x octs channel octets over <= 256 channels; grid = (channel blocks, slabs).  A thread sums at most a
+// few hundred rows (16-row fp32 partials, then fp32 totals); everything across threads and slabs is added in double.  Raw moments and
+// fp32 thread totals keep the kernel at 3 blocks per SM (it ran at 128 registers and 3.3 TB/s with per-element xhat and double totals).
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, const float* __restrict__ dy, int dy_cpitch, int dy_coff,
-                     int upsample2, int Ho, int Wo, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     const float* __restrict__ ab, int act, float* __restrict__ dres, int dres_cpitch,
+                     int upsample2, int Ho, int Wo, const float* __restrict__ ab, int act, float* __restrict__ dres, int dres_cpitch,
                      int dres_coff, int dres_accum, double* __restrict__ slab, unsigned int* __restrict__ gmax_bits) {
   const int cb = min(C, 256), octs = cb >> 3, lanes = 256 / octs;
   const int oc = threadIdx.x % octs, rl = threadIdx.x / octs;
   const int c = blockIdx.x * cb + oc * 8;
   const int per = (M + gridDim.y - 1) / gridDim.y;
   const int m0 = blockIdx.y * per, m1 = min(M, m0 + per);
-  double s0[8], s1[8];
+  float s0[8], s1[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s0[j] = 0.0; s1[j] = 0.0; }
+  for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
   float gm = 0.f;
   if (c < C && rl < lanes) {
-    float mu[8], rs[8], ga[8], be[8];
+    float ga[8], be[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { mu[j] = mean[c + j]; rs[j] = rstd[c + j]; ga[j] = ab[c + j]; be[j] = ab[C + c + j]; }
+    for (int j = 0; j < 8; ++j) { ga[j] = ab[c + j]; be[j] = ab[C + c + j]; }
     for (int mb = m0 + rl; mb < m1; mb += lanes * 16) {
       float f0[8], f1[8];
 #pragma unroll
@@ -330,9 +332,8 @@ bn_bwd_reduce_kernel(const __half* __restrict__ z, long long z_ps, int M, int C,
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xh = (zv[j] - mu[j]) * rs[j];
           const float gg = act_grad(g[j], fmaf(zv[j], ga[j], be[j]), act);        // u = a*z + b exactly as the forward computed it
-          f0[j] += gg; f1[j] = fmaf(gg, xh, f1[j]);
+          f0[j] += gg; f1[j] = fmaf(gg, zv[j], f1[j]);
           gm = fmaxf(gm, fabsf(gg));
         }
       }
@@ -346,7 +347,7 @@ bn_bwd_reduce_kernel(const __half* __restrict__ z, long long z_ps, int M, int C,
   for (int q = 0; q < 2; ++q) {
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = q == 0 ? s0[j] : s1[j];
+    for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = (double)(q == 0 ? s0[j] : s1[j]);
     __syncthreads();
     if (pow2) {
       for (int st = lanes >> 1; st >= 1; st >>= 1) {
@@ -380,8 +381,9 @@ bn_bwd_reduce_kernel(const __half* __restrict__ z, long long z_ps, int M, int C,
 
 // per channel: mean g, mean g*xhat, dgamma, dbeta (one warp per channel, fixed-order shuffle tree) and the layer's max|gamma*rstd|
 __global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const double* __restrict__ slab, int nslab, int M, int C, const float* __restrict__ ab, float* __restrict__ mg,
-                       float* __restrict__ dgamma, float* __restrict__ dbeta, unsigned int* __restrict__ amax_bits) {
+bn_bwd_finalize_kernel(const double* __restrict__ slab, int nslab, int M, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ ab, float* __restrict__ mg, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                       unsigned int* __restrict__ amax_bits) {
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s0 = 0.0, s1 = 0.0;
@@ -389,6 +391,7 @@ bn_bwd_finalize_kernel(const double* __restrict__ slab, int nslab, int M, int C,
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, o); s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o); }
   if (lane) return;
+  s1 = (double)rstd[c] * (s1 - (double)mean[c] * s0);         // sum g*xhat from the raw moments
   mg[c] = (float)(s0 / M); mg[C + c] = (float)(s1 / M);
   dbeta[c] = (float)s0; dgamma[c] = (float)s1;
   atomicMax(amax_bits, __float_as_uint(fabsf(ab[c])));        // order independent
@@ -413,7 +416,7 @@ __device__ __forceinline__ float dz_scale_from(const float* dzscale) {
 
 // dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)) * 2^s as fp16 planes (+ the zero-dilated copy for strided convolutions);
 // also zeroes the guard rows [M, M + kGuardRows) of dz.  Thread mapping as in bn_act_fwd_kernel.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, const float* __restrict__ mg, const float* __restrict__ dy,
                     int dy_cpitch, int dy_coff, int upsample2, int Ho, int Wo, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ ab, int act, float* __restrict__ dzscale,
@@ -425,8 +428,18 @@ bn_bwd_apply_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, 
   if (c >= C || rl >= lanes) return;
   const float s = dz_scale_from(dzscale);
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { dzscale[0] = s; dzscale[1] = 1.f / s; }   // read by the dgrad / wgrad epilogues
-  float mu[8], rs[8], a[8], b[8], m0[8], m1[8];
-  ld8_f32(mean + c, mu); ld8_f32(rstd + c, rs); ld8_f32(ab + c, a); ld8_f32(ab + C + c, b); ld8_f32(mg + c, m0); ld8_f32(mg + C + c, m1);
+  // dz*s = a*s*(gg - m0 - xhat*m1) = k1*gg + k2*z + k3 with per-channel constants (three registers per channel instead of six)
+  float a[8], b[8], k1[8], k2[8], k3[8];
+  {
+    float mu[8], rs[8], m0[8], m1[8];
+    ld8_f32(mean + c, mu); ld8_f32(rstd + c, rs); ld8_f32(ab + c, a); ld8_f32(ab + C + c, b); ld8_f32(mg + c, m0); ld8_f32(mg + C + c, m1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      k1[j] = a[j] * s;                                               // a = gamma * rstd
+      k2[j] = -k1[j] * m1[j] * rs[j];
+      k3[j] = k1[j] * (m1[j] * rs[j] * mu[j] - m0[j]);
+    }
+  }
   int sat = 0;
   for (int m = blockIdx.y * lanes + rl; m < M + kGuardRows; m += gridDim.y * lanes) {
     float o[8];
@@ -436,9 +449,8 @@ bn_bwd_apply_kernel(const __half* __restrict__ z, long long z_ps, int M, int C, 
       load_dy8(dy, dy_cpitch, dy_coff, upsample2, Ho, Wo, m, c, g);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float xh = (zv[j] - mu[j]) * rs[j];
         const float gg = act_grad(g[j], fmaf(zv[j], a[j], b[j]), act);
-        o[j] = a[j] * (gg - m0[j] - xh * m1[j]) * s;                  // a = gamma * rstd
+        o[j] = fmaf(k1[j], gg, fmaf(k2[j], zv[j], k3[j]));
       }
     } else {
 #pragma unroll
@@ -1186,10 +1198,10 @@ static int train_fwd_bwd(yolo_handle* h, const void* input, int in_layout, const
       const int cb = std::min(C, 256);
       const int red_lanes = 256 / (cb / 8);
       const int nslab = std::max(1, std::min(std::min(L.slab_cap, kSlabCtas / ((C + cb - 1) / cb)), M / (red_lanes * 16)));
-      bn_bwd_reduce_kernel<<<dim3((C + cb - 1) / cb, nslab), 256, 0, st>>>(L.z, L.z_ps, M, C, dy, dyp, op.out.coff, op.upsample2, L.Ho, L.Wo, L.mean,
-                                                                         L.rstd, L.ab, op.act, dres, op.has_res ? grad_pitch(op.res) : 0, op.res.coff,
+      bn_bwd_reduce_kernel<<<dim3((C + cb - 1) / cb, nslab), 256, 0, st>>>(L.z, L.z_ps, M, C, dy, dyp, op.out.coff, op.upsample2, L.Ho, L.Wo,
+                                                                         L.ab, op.act, dres, op.has_res ? grad_pitch(op.res) : 0, op.res.coff,
                                                                          L.dres_accum ? 1 : 0, L.slab, reinterpret_cast<unsigned int*>(L.dzscale + 2));
-      bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(L.slab, nslab, M, C, L.ab, L.mg, T->G + L.o_gamma, T->G + L.o_beta,
+      bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(L.slab, nslab, M, C, L.mean, L.rstd, L.ab, L.mg, T->G + L.o_gamma, T->G + L.o_beta,
                                                           reinterpret_cast<unsigned int*>(L.dzscale + 3));
       {
         const int lanes = 256 / (cb / 8);
