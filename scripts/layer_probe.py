@@ -15,7 +15,7 @@ import yolo_b200  # noqa: E402
 B, H, W, cin, cout, k, stride, pad = (int(v) for v in sys.argv[1].split(","))
 variants = [dict(kv.split("=") for kv in a.split(",") if "=" in kv) for a in sys.argv[2:]] or [{}]
 keys = sorted({k_ for v in variants for k_ in v})
-spec = dict(size=[H, W], cin=cin, cout=cout, k=k, stride=stride, pad=pad, act=1, residual=2, bn=1)
+spec = dict(size=[H, W], cin=cin, cout=cout, k=k, stride=stride, pad=pad, act=1, residual=int(os.environ.get("RES", "2")), bn=1)      # RES=1: + input (cin == cout)
 net = yolo_b200.Net("debugconv", spec, precision=os.environ.get("PREC", "fp16x3"), max_batch=B)
 rng = np.random.default_rng(0)
 params = {}

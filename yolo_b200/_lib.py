@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyolo_b200.so")
+LIB_PATH = os.environ.get("YOLO_B200_LIB") or os.path.join(_HERE, "libyolo_b200.so")      # override: A/B runs of two builds
 
 MAX_STAGES, MAX_SCALES, MAX_ANCHORS, MAX_BLOCKS = 8, 3, 8, 8
 NET_CARNET, NET_CARLPNET, NET_LPDENSENET, NET_DEBUGCONV, NET_CARDENSENET = 0, 1, 2, 3, 4
