@@ -43,7 +43,7 @@ def main():
     # the LAST complete step of the capture: 75 conv launches + decode_kernel<0>
     last = [i for i, n in enumerate(names) if "decode_kernel" in n][-1]
     order = rows[last - 75:last + 1]
-    assert "stem3x3" in order[0][4], order[0][4]
+    assert "stem" in order[0][4], order[0][4]
     convs = dk53_convs()
     ci, tot, tot_fl = 0, 0.0, 0.0
     groups = {}

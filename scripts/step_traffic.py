@@ -35,7 +35,7 @@ def main():
             launches[lid]["tensor_pct"] = float(value.replace(",", ""))
     names = [launches[i]["name"] for i in order]
     last = max(i for i, n in enumerate(names) if "decode_kernel" in n)
-    stems = [i for i, n in enumerate(names[:last]) if "stem3x3" in n]
+    stems = [i for i, n in enumerate(names[:last]) if "stem" in n]
     first = max(stems) if stems else max(0, last - 75)          # a capture filtered to the tcgen05 kernel has no stem launch
     step = [launches[i] for i in order[first:last + 1]]
     conv = [l for l in step if "decode_kernel" not in l["name"]]
