@@ -61,6 +61,11 @@ struct UmmaParams {
   int dbg_nostore;                          // timing experiments: 1 = skip the epilogue's 16-bit stores, 2 = skip the epilogue (wrong results)
   int dbg_pairs;                            // >0: issue only the first n plane pairs (timing experiments; wrong results)
   int a_tiled;                              // 1x1/s1/p0: activations are a plain [pixels][channels] matrix -> tiled TMA, not im2col
+  // split-K tail launches: n_tiles counts work UNITS = (tile, K split); unit u works on tile tile_begin + u / ksplit over the k-blocks
+  // [split * nkb / ksplit, (split + 1) * nkb / ksplit) and stores its raw fp32 partial tile to out + split * split_stride, rows
+  // counted from row_begin (ksplit = 1, tile_begin = row_begin = 0: the ordinary launch)
+  int ksplit, tile_begin, row_begin;
+  long long split_stride;
   long long a_plane_rows;                   // pixel rows per plane in that matrix (= max_batch*H*W)
   // epilogue
   float acc_scale;                          // power of two undoing the weight pre-scale (exact)
@@ -163,7 +168,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // TMEM: two partial buffers for the leading product + two correction buffers (tile parity), each `acc_stride` columns
   const int acc_stride = WIDE ? 256 : (p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : 128));
   const int tmem_cols = WIDE ? 512 : (HAS_CORR ? 4 * acc_stride : (2 * acc_stride < 32 ? 32 : 2 * acc_stride));
-  const int nkb = p.taps * p.cin_blocks;
+  const int nkb = p.taps * p.cin_blocks / p.ksplit;                // k-blocks per work unit (the host keeps ksplit a divisor)
   const int npart = (nkb + p.flush - 1) / p.flush;
 
   if (threadIdx.x == 0) {
@@ -201,7 +206,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       const int HoWo = p.Ho * p.Wo;
-      for (int tile = sched_id; tile < p.n_tiles; tile += sched_n) {
+      for (int unit = sched_id; unit < p.n_tiles; unit += sched_n) {
+        const int tile = p.tile_begin + unit / p.ksplit, kb0 = (unit % p.ksplit) * nkb;
         const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
         const int n0 = nt * p.BN + (PAIR ? (int)cta_rank * b_rows : 0);
         const int m0 = (PAIR ? mt * 2 + (int)cta_rank : mt) * TILE_M;
@@ -209,7 +215,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int rem = m0 - img * HoWo;
         const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
         const int bw = ow * p.stride - p.pad, bh = oh * p.stride - p.pad;          // receptive-field origin of the first pixel
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kbl = 0; kbl < nkb; ++kbl) {
+          const int kb = kb0 + kbl;
           const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
           const int r = tap / p.kw, s = tap - r * p.kw;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -385,7 +392,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // not start waiting for its partials before the other group has consumed all of the preceding tile's partials:
     // named barriers 3/4 pass the turn (FA3-style ping-pong); group 1 donates the first turn to group 0.
     if (!WIDE && group == 1) asm volatile("bar.arrive 3, 256;" ::: "memory");
-    for (int tile = sched_id + (WIDE ? 0 : group * sched_n); tile < p.n_tiles; tile += (WIDE ? 1 : 2) * sched_n, it += (WIDE ? 1 : 2)) {
+    for (int unit = sched_id + (WIDE ? 0 : group * sched_n); unit < p.n_tiles; unit += (WIDE ? 1 : 2) * sched_n, it += (WIDE ? 1 : 2)) {
+      const int tile = p.tile_begin + unit / p.ksplit, split = unit % p.ksplit;
       const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
       const int m0 = (PAIR ? mt * 2 + (int)cta_rank : mt) * TILE_M;
       const int n0 = nt * p.BN + (WIDE ? group * 128 : 0);
@@ -478,12 +486,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int q = p.upsample2 == 1 ? 0 : p.upsample2 - 2;
             rpix[i] = (img * 2 * p.Ho + 2 * oh + (q >> 1)) * (2 * p.Wo) + 2 * ow + (q & 1);
           } else {
-            rpix[i] = mr;
+            rpix[i] = mr - p.row_begin;
           }
         }
       }
       unsigned char* s_stage = s_stage_all + (warp - 2) * STAGE_OUT_BYTES;
-      size_t pix0 = (size_t)m;                              // fp32 outputs: this thread's own row
+      size_t pix0 = (size_t)(m - p.row_begin);              // fp32 outputs: this thread's own row
       if (OUT_F32 && p.upsample2 > 1) {
         const int img = m / HoWo, rem = m - img * HoWo;
         const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
@@ -545,10 +553,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
         if (OUT_F32) {                                      // head convs: fp32 NHWC == (B, H*W, A, C); gradient buffers (accum)
-          float* op = static_cast<float*>(p.out) + pix0 * p.out_cpitch + p.out_coff + nb;
+          float* op = static_cast<float*>(p.out) + (size_t)split * p.split_stride + pix0 * p.out_cpitch + p.out_coff + nb;
           if (f32_tr) {
             const int g = lane & 3, sw = (lane >> 1) & 3;
-            float* obase = static_cast<float*>(p.out) + p.out_coff + nb + g * 4;
+            float* obase = static_cast<float*>(p.out) + (size_t)split * p.split_stride + p.out_coff + nb + g * 4;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               __syncwarp();
@@ -674,6 +682,63 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// Split-K fix-up: sums the fp32 partial tiles of the K splits in a FIXED order (deterministic), applies the BN affine, activation and
+// residual, and writes the fp16 planes.  One thread per (row, 8 channels); only tiles of the tail [tile_begin, ...) are touched.
+__global__ void __launch_bounds__(256)
+splitk_fixup_kernel(const float* __restrict__ ws, int ksplit, long long split_stride, int row_begin, int M, int Cout, int tile_begin,
+                    int n_tiles_n, int BN, int rows_per_tile, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                    const unsigned short* __restrict__ res, int res_cpitch, int res_coff, long long res_ps, unsigned short* __restrict__ out,
+                    int out_cpitch, int out_coff, long long out_ps, int* sat_flag) {
+  const int oct = Cout >> 3;
+  const long long total = (long long)(M - row_begin) * oct;
+  int sat = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int rl = (int)(i / oct), c = (int)(i - (long long)rl * oct) * 8;
+    const int m = row_begin + rl;
+    if ((m / rows_per_tile) * n_tiles_n + c / BN < tile_begin) continue;       // this tile belongs to the full-K launch
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = 0.f;
+    for (int sp = 0; sp < ksplit; ++sp) {
+      const float4* q = reinterpret_cast<const float4*>(ws + (size_t)sp * split_stride + (size_t)rl * Cout + c);
+      const float4 a = q[0], b = q[1];
+      y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; y[4] += b.x; y[5] += b.y; y[6] += b.z; y[7] += b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(y[j], scale ? __ldg(scale + c + j) : 1.f, shift ? __ldg(shift + c + j) : 0.f);
+      t = act == ACT_LEAKY ? fmaxf(t, 0.1f * t) : (act == ACT_RELU ? fmaxf(t, 0.f) : t);
+      y[j] = t;
+    }
+    if (res) {
+      const unsigned short* rp = res + (size_t)m * res_cpitch + res_coff + c;
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(rp)), l = __ldg(reinterpret_cast<const uint4*>(rp + res_ps));
+      const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hh[e])), b = __half22float2(*reinterpret_cast<const __half2*>(&ll[e]));
+        y[2 * e] += a.x + b.x;
+        y[2 * e + 1] += a.y + b.y;
+      }
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (fmaxf(fabsf(y[2 * e]), fabsf(y[2 * e + 1])) > kF16Max) sat = 1;
+      uint32_t h;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(y[2 * e + 1]), "f"(y[2 * e]));
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+      const __half2 l2 = __floats2half2_rn(y[2 * e] - f.x, y[2 * e + 1] - f.y);
+      hi[e] = h;
+      lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    unsigned short* op = out + (size_t)m * out_cpitch + out_coff + c;
+    *reinterpret_cast<uint4*>(op) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(op + out_ps) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  if (sat && sat_flag) atomicOr(sat_flag, YOLO_SAT_ACT_CONV);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -699,7 +764,7 @@ int load_tma_entry_points(void** tiled, void** im2col) {
 
 // Experiment switches are read ONCE per process (they used to be getenv calls on every launch).
 struct UmmaEnv {
-  bool disable, wide, pairwide, a_tiled;
+  bool disable, wide, pairwide, a_tiled, splitk;
   int hhlast;        // -1 default, 0 / 1 forced
   int flush;         // 0 default
   int dbg_pairs, dbg_nostore;
@@ -711,6 +776,7 @@ static const UmmaEnv& umma_env() {
     auto num = [](const char* n, int dflt) { const char* v = getenv(n); return v ? atoi(v) : dflt; };
     UmmaEnv x;
     x.disable = flag("YOLO_B200_DISABLE_UMMA", false);
+    x.splitk = flag("YOLO_B200_SPLITK", true);
     x.wide = flag("YOLO_B200_WIDE", true);
     x.pairwide = flag("YOLO_B200_PAIRWIDE", true);
     x.a_tiled = flag("YOLO_B200_A_TILED", true);
@@ -1013,6 +1079,8 @@ int umma_build_maps(UmmaConv& u, void* in_base, int max_batch, int H, int W, int
 }
 
 void umma_release(UmmaConv& u) {
+  if (u.split_ws) cudaFree(u.split_ws);
+  u.split_ws = nullptr; u.split_ws_bytes = 0;
   if (u.w_packed) cudaFree(u.w_packed);
   u.w_packed = nullptr;
   u.eligible = u.enabled = false;
@@ -1167,6 +1235,64 @@ int launch_conv_umma(const UmmaConv& u, const ConvDesc& d, cudaStream_t st, Umma
   if (d.res && ((d.res_cpitch | d.res_coff) & 7)) return fail(YOLO_E_UNSUPPORTED, "umma: residual needs 16-byte aligned channel slices");
   if (d.res && (d.Cout % 32 || d.out_dtype == DT_F32)) return fail(YOLO_E_UNSUPPORTED, "umma: residual needs Cout %% 32 == 0 and a 16-bit activation format");
   const int smem_bytes = 1024 + stages * stage_bytes + aux_bytes;
+  p.ksplit = 1;
+  // ---- split-K tail (inference, fp16x3, 16-bit output).  A persistent grid of S scheduling units runs tiles / S waves; the last
+  // wave of the 13^2 and 26^2 maps is mostly empty (512->1024 @13^2, batch 32: 88 tiles on 74 CTA pairs = two waves for 1.19 waves
+  // of work).  The full waves run as before; the tail tiles are split along K into `ksplit` units each (a divisor of the k-block
+  // count, tail * ksplit <= S), every unit writes its raw fp32 partial tile into a per-layer scratch, and a small fix-up kernel adds
+  // the splits in a fixed order and does the epilogue.  Batch-1 frames (every layer is "tail") gain the most.
+  if (env.splitk && mode == 2 && !ex && d.out_dtype == DT_F16X2 && !d.upsample2 && p.dbg_nostore == 0 && p.dbg_pairs == 0 && d.Cout % 8 == 0) {
+    const int S = kind == 6 ? num_sms / 2 : num_sms;
+    const int full = (p.n_tiles / S) * S, tail = p.n_tiles - full;
+    const int nkb = p.taps * p.cin_blocks;
+    int ksplit = 1;
+    if (tail > 0 && 2 * tail <= S)
+      for (int k = 2; k <= 16 && tail * k <= S; ++k)
+        if (nkb % k == 0 && nkb / k >= 2) ksplit = k;
+    const int rows_per_tile = kind == 6 ? 2 * TILE_M : TILE_M;
+    if (ksplit > 1) {
+      // worth it only where the saved part of the last wave outweighs a second conv launch (~20 us of prologue, pipeline fill and
+      // epilogue) plus the fix-up (5-12 us): measured per layer in profiles/r2_splitk.txt - the 1x1 and 104^2/208^2 layers lose
+      const double wave_us = 2.0 * rows_per_tile * p.BN * (double)nkb * p.bk * 3.0 / (kind == 6 ? 18.4e6 : 9.2e6);   // MMA time of one full-K tile
+      const double gain_us = wave_us * (1.0 - 1.0 / ksplit);
+      if (gain_us < (full > 0 ? 30.0 : 8.0)) ksplit = 1;
+    }
+    if (ksplit > 1) {
+      const int row_begin = (full / p.n_tiles_n) * rows_per_tile;
+      const size_t rows = (size_t)(p.M - row_begin);
+      const size_t need = (size_t)ksplit * rows * d.Cout * sizeof(float);
+      if (u.split_ws_bytes < need) {                       // per-layer scratch, grown on first use (warm-up), freed by umma_release
+        if (u.split_ws) cudaFree(u.split_ws);
+        u.split_ws = nullptr; u.split_ws_bytes = 0;
+        if (cudaMalloc(&u.split_ws, need) != cudaSuccess) { cudaGetLastError(); ksplit = 1; }
+        else u.split_ws_bytes = need;
+      }
+      if (ksplit > 1) {
+        if (full > 0) {
+          UmmaParams pa = p;
+          pa.n_tiles = full;
+          switch (mode) { default: rc = launch_mode<2>(u, pa, kind, smem_bytes, num_sms, st); }
+          if (rc) return rc;
+        }
+        UmmaParams pb = p;
+        pb.n_tiles = tail * ksplit; pb.ksplit = ksplit; pb.tile_begin = full; pb.row_begin = row_begin;
+        pb.split_stride = (long long)rows * d.Cout;
+        pb.scale = nullptr; pb.shift = nullptr; pb.act = ACT_NONE; pb.res = nullptr;
+        pb.out = u.split_ws; pb.out_dtype = DT_F32; pb.out_cpitch = d.Cout; pb.out_coff = 0; pb.sat_flag = nullptr;
+        rc = launch_mode<2>(u, pb, kind, smem_bytes, num_sms, st);
+        if (rc) return rc;
+        const long long total = (long long)rows * (d.Cout / 8);
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+        splitk_fixup_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(u.split_ws), ksplit, pb.split_stride, row_begin, p.M, d.Cout, full,
+                                                    p.n_tiles_n, p.BN, rows_per_tile, d.scale, d.shift, d.act,
+                                                    static_cast<const unsigned short*>(d.res), d.res_cpitch, d.res_coff, d.res_plane_stride,
+                                                    static_cast<unsigned short*>(d.out), d.out_cpitch, d.out_coff, d.out_plane_stride, d.sat_flag);
+        ++g_launches;
+        YB_CUDA(cudaGetLastError());
+        return YOLO_OK;
+      }
+    }
+  }
   switch (mode) {
     case 0: return launch_mode<0>(u, p, kind, smem_bytes, num_sms, st);
     case 1: return launch_mode<1>(u, p, kind, smem_bytes, num_sms, st);

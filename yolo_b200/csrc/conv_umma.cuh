@@ -26,6 +26,8 @@ struct UmmaConv {
   bool c32i = false;          // Cin = 32, plane-interleaved activations ([hi(32) | lo(32)] per pixel): KIND 7
   float prescale = 1.f;      // 2^s applied to the weights when they are packed (fp16 planes stay normal)
   float acc_scale = 1.f;     // 2^-s, undone in the epilogue
+  mutable void* split_ws = nullptr;   // split-K partial tiles of this layer's tail wave (grown on first use)
+  mutable size_t split_ws_bytes = 0;
 };
 
 // optional epilogue extras of the training step
