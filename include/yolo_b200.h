@@ -139,7 +139,9 @@ int  yolo_param_info(const yolo_handle* h, int index, const char** name, int32_t
 int  yolo_load_param(yolo_handle* h, const char* name, const float* host, size_t n_elems);
 int  yolo_finalize_params(yolo_handle* h, void* stream);   /* fold BN, repack, upload; requires all params */
 
-/* Activation workspace: caller-owned device memory (e.g. a torch uint8 tensor). */
+/* Activation workspace: caller-owned device memory (e.g. a torch uint8 tensor).  Besides it the handle owns, on its device, the
+ * folded parameters and packed weight planes and - allocated on the first forward that needs them, released by yolo_destroy - small
+ * per-layer scratch buffers for the split-K partial tiles of the convolution's last wave (a few MB per layer). */
 size_t yolo_workspace_bytes(const yolo_handle* h, int batch);
 int  yolo_set_workspace(yolo_handle* h, void* device_ptr, size_t bytes);
 

@@ -40,10 +40,28 @@ def main():
     rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10 and r[0].isdigit()]
     passes = float(sys.argv[2]) if len(sys.argv) > 2 else 3
     names = [r[4] for r in rows]
-    # the LAST complete step of the capture: 75 conv launches + decode_kernel<0>
+    # the LAST complete step of the capture: 75 conv layers + decode_kernel<0>.  A layer with a split-K tail is three launches
+    # (full waves, split tail with fp32 partial output, fix-up) - or two when it has no full wave; they are merged into one row.
     last = [i for i, n in enumerate(names) if "decode_kernel" in n][-1]
-    order = rows[last - 75:last + 1]
-    assert "stem" in order[0][4], order[0][4]
+    first = max(i for i, n in enumerate(names[:last]) if "stem" in n)
+    raw = rows[first:last + 1]
+    order, i = [], 0
+    while i < len(raw):
+        r = list(raw[i])
+        j = i + 1
+        while j < len(raw) and "splitk_fixup" not in raw[i][4] and "decode" not in raw[i][4]:
+            nxt = raw[j][4]
+            is_tail = "conv_umma_kernel<2, 1," in nxt.replace("yb::", "") or "conv_umma_kernel<(int)2, (bool)1" in nxt
+            if "splitk_fixup" in nxt or (is_tail and j + 1 < len(raw) and "splitk_fixup" in raw[j + 1][4]):
+                r[-1] = str(float(r[-1]) + float(raw[j][-1]))
+                j += 1
+                if "splitk_fixup" in nxt:
+                    break
+            else:
+                break
+        order.append(r)
+        i = j
+    assert "stem" in order[0][4] and len(order) == 76, (order[0][4], len(order))
     convs = dk53_convs()
     ci, tot, tot_fl = 0, 0.0, 0.0
     groups = {}
